@@ -1,0 +1,1449 @@
+// mmidx.cu -- host runtime + C ABI of libmmidx.so (see include/mmidx.h).
+//
+// Index objects own their HBM storage:
+//   Linear : vectors packed in blocks of 32 (dimension-major inside a block)      Linear.java:34,80 vectorsList
+//   PQ     : flat code array [n][code_bytes], iid == position                     PQ.java:65,71 pqByteCodes/pqShortCodes
+//   IVFPQ  : append log (codes + list ids in iid order) and, once sealed, a CSR copy grouped by list in
+//            insertion order with 16-entry aligned list starts                    IVFPQ.java:72-83 invertedLists/pqByteCodes[l]
+// There is no CPU compute path: every entry point that does arithmetic launches the sm_100a kernels.
+#include "../../include/mmidx.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "tie_resolve.cuh"
+
+using namespace mmidx;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(MMIDX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define RET(call)                 \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != MMIDX_OK) return r_; \
+    } while (0)
+
+extern "C" const char *mmidx_last_error(void) { return g_err.c_str(); }
+extern "C" const char *mmidx_version(void) { return "libmmidx 0.1 sm_100a"; }
+
+// ---------------------------------------------------------------------------------------------------------
+// device buffers
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    // grow to at least `bytes`, keeping the first `keep` bytes
+    int reserve(size_t bytes, size_t keep, cudaStream_t st) {
+        if (bytes <= cap) return MMIDX_OK;
+        size_t ncap = std::max(bytes, cap + cap / 2);
+        ncap = (ncap + 255) & ~(size_t)255;
+        void *np = nullptr;
+        CK(cudaMalloc(&np, ncap));
+        if (p && keep) CK(cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return MMIDX_OK;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// stream-ordered scratch, released (stream-ordered) when the call returns
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() {
+        for (void *p : ptrs) cudaFreeAsync(p, st);
+    }
+    template <typename T>
+    int get(T **out, size_t count) {
+        void *p = nullptr;
+        size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+        CK(cudaMallocAsync(&p, bytes, st));
+        ptrs.push_back(p);
+        *out = reinterpret_cast<T *>(p);
+        return MMIDX_OK;
+    }
+};
+
+struct StageTimer {
+    // events bracket stages of every chunk; summed lazily by mmidx_last_timings
+    struct Span {
+        cudaEvent_t a, b;
+        int stage;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    bool enabled = false;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void reset() {
+        spans.clear();
+        used = 0;
+    }
+    ~StageTimer() {
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
+struct mmidx_index {
+    mmidx_params p;
+    int S = 0, code_bytes = 0, device = 0;
+    int shard_rank = 0, shard_count = 1;
+    bool has_P = false, has_C = false, has_perm = false;
+    DevBuf dP, dC, dCt, dperm;
+    int64_t n = 0;        // loadCounter: vectors offered to the index (global iid counter)
+    int64_t n_local = 0;  // vectors stored on this shard
+    // Linear
+    DevBuf dXb;
+    // PQ flat / IVFPQ append log
+    DevBuf dcodes;
+    std::vector<int32_t> h_list;  // IVFPQ: list id of every stored entry, log order
+    std::vector<int32_t> h_iid;   // IVFPQ: global iid of every stored entry, log order
+    // IVFPQ CSR
+    bool sealed = false;
+    DevBuf csr_codes, csr_iids, dlist_off, dlist_len;
+    std::vector<int32_t> h_list_len;
+    std::vector<int64_t> h_list_off;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    StageTimer timer;
+    int last_launches = 0;
+    size_t lut_chunk_bytes = (size_t)64 << 20;
+};
+
+struct Launches {
+    int n = 0;
+};
+
+static int check_device(int device) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0)
+        return fail(MMIDX_ERR_CUDA, "no CUDA device: libmmidx has no CPU path (%s)", cudaGetErrorString(e));
+    if (device >= cnt) return fail(MMIDX_ERR_CUDA, "device %d out of range (%d devices)", device, cnt);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MMIDX_ERR_CUDA, "device %d is sm_%d%d; libmmidx is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    return MMIDX_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return fail(MMIDX_ERR_UNSUPPORTED, "kernel needs %zu bytes of shared memory", bytes);
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return MMIDX_OK;
+}
+
+static int post_launch(const char *name, int *launches) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MMIDX_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+    if (launches) ++*launches;
+    return MMIDX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mmidx_create(const mmidx_params *pp, mmidx_t **out) {
+    if (!pp || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    mmidx_params p = *pp;
+    if (p.type < MMIDX_LINEAR || p.type > MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "unknown index type %d", p.type);
+    if (p.d < 1) return fail(MMIDX_ERR_DIM, "vectorLength must be >= 1");
+    if (p.max_n < 0) return fail(MMIDX_ERR_INVALID, "maxNumVectors < 0");
+    if (p.type != MMIDX_LINEAR) {
+        // PQ.java:148-150: "The given number of subvectors is not valid!"
+        if (p.m < 1 || p.d % p.m != 0) return fail(MMIDX_ERR_DIM, "The given number of subvectors is not valid!");
+        if (p.ks < 1 || p.ks > 65536) return fail(MMIDX_ERR_UNSUPPORTED, "numProductCentroids must be in 1..65536");
+    }
+    if (p.type == MMIDX_IVFPQ) {
+        if (p.nlist < 1) return fail(MMIDX_ERR_INVALID, "numCoarseCentroids must be >= 1");
+        if (p.w <= 0) p.w = (int)(p.nlist * 0.1);  // IVFPQ.java:188
+    }
+    int device = p.device;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    RET(check_device(device));
+    DeviceGuard g(device);
+    mmidx_index *ix = new mmidx_index();
+    ix->p = p;
+    ix->device = device;
+    ix->S = (p.type == MMIDX_LINEAR) ? 0 : p.d / p.m;
+    ix->code_bytes = (p.type == MMIDX_LINEAR) ? 0 : (p.ks <= 256 ? p.m : 2 * p.m);
+    ix->shard_count = p.shard_count > 1 ? p.shard_count : 1;
+    ix->shard_rank = p.shard_count > 1 ? p.shard_rank : 0;
+    if (ix->shard_rank < 0 || ix->shard_rank >= ix->shard_count) {
+        delete ix;
+        return fail(MMIDX_ERR_INVALID, "shard_rank out of range");
+    }
+    if (const char *e = getenv("MMIDX_LUT_CHUNK_MB")) {
+        long v = atol(e);
+        if (v >= 1) ix->lut_chunk_bytes = (size_t)v << 20;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ix;
+        return fail(MMIDX_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    // keep freed scratch in the pool: search calls re-use it without going back to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (p.type == MMIDX_IVFPQ) {
+        ix->h_list_len.assign(p.nlist, 0);
+        ix->h_list_off.assign(p.nlist, 0);
+    }
+    *out = ix;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_destroy(mmidx_t *ix) {
+    if (!ix) return MMIDX_OK;
+    {
+        DeviceGuard g(ix->device);
+        if (ix->stream) {
+            cudaStreamSynchronize(ix->stream);
+            cudaStreamDestroy(ix->stream);
+        }
+    }
+    DeviceGuard g(ix->device);
+    delete ix;
+    return MMIDX_OK;
+}
+
+__global__ void k_transpose(const double *__restrict__ A, int rows, int cols, double *__restrict__ At) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)rows * cols) return;
+    int r = (int)(e / cols), c = (int)(e - (int64_t)r * cols);
+    At[(int64_t)c * rows + r] = A[e];
+}
+
+extern "C" int mmidx_set_product_quantizer(mmidx_t *ix, const double *P) {
+    if (!ix || !P) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type == MMIDX_LINEAR) return fail(MMIDX_ERR_INVALID, "Linear index has no product quantizer");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    size_t bytes = sizeof(double) * (size_t)ix->p.m * ix->p.ks * ix->S;
+    RET(ix->dP.reserve(bytes, 0, ix->stream));
+    CK(cudaMemcpyAsync(ix->dP.p, P, bytes, cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    ix->has_P = true;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C) {
+    if (!ix || !C) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "only IVFPQ has a coarse quantizer");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    size_t cnt = (size_t)ix->p.nlist * ix->p.d;
+    RET(ix->dC.reserve(cnt * sizeof(double), 0, ix->stream));
+    RET(ix->dCt.reserve(cnt * sizeof(double), 0, ix->stream));
+    CK(cudaMemcpyAsync(ix->dC.p, C, cnt * sizeof(double), cudaMemcpyHostToDevice, ix->stream));
+    k_transpose<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->stream>>>(ix->dC.as<double>(), ix->p.nlist, ix->p.d,
+                                                                      ix->dCt.as<double>());
+    RET(post_launch("k_transpose", nullptr));
+    CK(cudaStreamSynchronize(ix->stream));
+    ix->has_C = true;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm) {
+    if (!ix) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type == MMIDX_LINEAR) return fail(MMIDX_ERR_INVALID, "Linear index takes no transformation");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!perm) {
+        ix->has_perm = false;
+        return MMIDX_OK;
+    }
+    std::vector<char> seen(ix->p.d, 0);
+    for (int i = 0; i < ix->p.d; ++i) {
+        if (perm[i] < 0 || perm[i] >= ix->p.d || seen[perm[i]]) return fail(MMIDX_ERR_INVALID, "perm is not a permutation of 0..d-1");
+        seen[perm[i]] = 1;
+    }
+    RET(ix->dperm.reserve(sizeof(int32_t) * (size_t)ix->p.d, 0, ix->stream));
+    CK(cudaMemcpyAsync(ix->dperm.p, perm, sizeof(int32_t) * (size_t)ix->p.d, cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    ix->has_perm = true;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_set_w(mmidx_t *ix, int32_t w) {
+    if (!ix) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "setW applies to IVFPQ only");
+    ix->p.w = w;  // validated at search time, like the reference (IVFPQ.java:95-97 stores it blindly)
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_enable_timings(mmidx_t *ix, int32_t on) {
+    if (!ix) return fail(MMIDX_ERR_INVALID, "null argument");
+    ix->timer.enabled = on != 0;
+    return MMIDX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// encode (K1c + K6)
+// ---------------------------------------------------------------------------------------------------------
+static int launch_assign(const double *dA, const double *dBt, int64_t na, int nb, int d, int32_t *dout, cudaStream_t st,
+                         int *launches) {
+    if (na == 0) return MMIDX_OK;
+    k_assign_nearest<<<(unsigned)((na + QT - 1) / QT), MMIDX_NT, 0, st>>>(dA, dBt, na, nb, d, dout);
+    return post_launch("k_assign_nearest", launches);
+}
+
+static int launch_pq_encode(mmidx_index *ix, const double *dX, const int32_t *dlist, int64_t n, uint8_t *dout,
+                            cudaStream_t st, int *launches) {
+    if (n == 0) return MMIDX_OK;
+    const int S = ix->S, m = ix->p.m, ks = ix->p.ks, d = ix->p.d;
+    const double *C = dlist ? ix->dC.as<double>() : nullptr;
+    const int32_t *perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
+    const double *P = ix->dP.as<double>();
+    dim3 grid((unsigned)((n + MMIDX_NT - 1) / MMIDX_NT), m);
+    int cchunk = std::min(ks, std::max(1, (32 * 1024) / (S * 8)));
+    size_t smem = (size_t)cchunk * S * sizeof(double);
+#define ENC(SV)                                                                                              \
+    case SV:                                                                                                 \
+        k_pq_encode<SV><<<grid, MMIDX_NT, smem, st>>>(dX, C, dlist, perm, P, n, d, m, ks, cchunk, dout, ix->code_bytes); \
+        break;
+    switch (S) {
+        ENC(1) ENC(2) ENC(4) ENC(8) ENC(16) ENC(32)
+        default:
+            k_pq_encode_generic<<<grid, MMIDX_NT, 0, st>>>(dX, C, dlist, perm, P, n, d, m, ks, S, dout, ix->code_bytes);
+    }
+#undef ENC
+    return post_launch("k_pq_encode", launches);
+}
+
+// encode n device-resident vectors: dlist (IVFPQ) and dcodes receive the assignment
+static int encode_dev(mmidx_index *ix, const double *dX, int64_t n, int32_t *dlist, uint8_t *dcodes, cudaStream_t st,
+                      int *launches) {
+    if (ix->p.type == MMIDX_IVFPQ) {
+        RET(launch_assign(dX, ix->dCt.as<double>(), n, ix->p.nlist, ix->p.d, dlist, st, launches));
+        RET(launch_pq_encode(ix, dX, dlist, n, dcodes, st, launches));
+    } else {
+        RET(launch_pq_encode(ix, dX, nullptr, n, dcodes, st, launches));
+    }
+    return MMIDX_OK;
+}
+
+static int require_quantizers(mmidx_index *ix) {
+    if (ix->p.type != MMIDX_LINEAR && !ix->has_P) return fail(MMIDX_ERR_STATE, "product quantizer not loaded");
+    if (ix->p.type == MMIDX_IVFPQ && !ix->has_C) return fail(MMIDX_ERR_STATE, "coarse quantizer not loaded");
+    return MMIDX_OK;
+}
+
+static const int64_t ADD_BATCH = 1 << 16;
+
+static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes, bool store) {
+    if (!ix || (n > 0 && !X)) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (n < 0) return fail(MMIDX_ERR_INVALID, "n < 0");
+    RET(require_quantizers(ix));
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    // ASS.java:232-235: indexVector returns false once loadCounter >= maxNumVectors
+    if (store && ix->n + n > ix->p.max_n) return fail(MMIDX_ERR_FULL, "Maximum index capacity reached");
+    cudaStream_t st = ix->stream;
+    const int d = ix->p.d;
+    int launches = 0;
+    if (ix->p.type == MMIDX_LINEAR) {
+        if (!store) return fail(MMIDX_ERR_INVALID, "Linear index has no codes to encode");
+        int64_t total = ix->n + n;
+        int64_t cap_vec = ((total + 31) / 32) * 32;
+        RET(ix->dXb.reserve((size_t)cap_vec * d * sizeof(double), (size_t)(((ix->n + 31) / 32) * 32) * d * sizeof(double), st));
+        Scratch sc(st);
+        double *dX;
+        RET(sc.get(&dX, (size_t)std::min(n, ADD_BATCH) * d));
+        for (int64_t b = 0; b < n; b += ADD_BATCH) {
+            int64_t nb = std::min(ADD_BATCH, n - b);
+            CK(cudaMemcpyAsync(dX, X + b * d, sizeof(double) * (size_t)nb * d, cudaMemcpyHostToDevice, st));
+            k_linear_pack<<<(unsigned)((nb * d + 255) / 256), 256, 0, st>>>(dX, nb, d, ix->n + b, ix->dXb.as<double>());
+            RET(post_launch("k_linear_pack", &launches));
+            CK(cudaStreamSynchronize(st));
+        }
+        ix->n += n;
+        ix->n_local = ix->n;
+        ix->last_launches = launches;
+        return MMIDX_OK;
+    }
+    const int cb = ix->code_bytes;
+    Scratch sc(st);
+    double *dX;
+    int32_t *dlist = nullptr;
+    uint8_t *dcodes;
+    int64_t *dsel = nullptr;
+    const int64_t bmax = std::min(std::max<int64_t>(n, 1), ADD_BATCH);
+    RET(sc.get(&dX, (size_t)bmax * d));
+    RET(sc.get(&dcodes, (size_t)bmax * cb));
+    if (ix->p.type == MMIDX_IVFPQ) RET(sc.get(&dlist, (size_t)bmax));
+    if (ix->shard_count > 1) RET(sc.get(&dsel, (size_t)bmax));
+    std::vector<int32_t> hl;
+    std::vector<int64_t> hsel;
+    for (int64_t b = 0; b < n; b += ADD_BATCH) {
+        int64_t nb = std::min(ADD_BATCH, n - b);
+        CK(cudaMemcpyAsync(dX, X + b * d, sizeof(double) * (size_t)nb * d, cudaMemcpyHostToDevice, st));
+        RET(encode_dev(ix, dX, nb, dlist, dcodes, st, &launches));
+        if (out_codes)
+            CK(cudaMemcpyAsync((uint8_t *)out_codes + b * cb, dcodes, (size_t)nb * cb, cudaMemcpyDeviceToHost, st));
+        if (ix->p.type == MMIDX_IVFPQ) {
+            hl.resize(nb);
+            CK(cudaMemcpyAsync(hl.data(), dlist, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (out_list) memcpy(out_list + b, hl.data(), sizeof(int32_t) * (size_t)nb);
+        }
+        if (store) {
+            if (ix->p.type == MMIDX_PQ) {
+                RET(ix->dcodes.reserve((size_t)(ix->n_local + nb) * cb, (size_t)ix->n_local * cb, st));
+                CK(cudaMemcpyAsync(ix->dcodes.as<uint8_t>() + ix->n_local * cb, dcodes, (size_t)nb * cb,
+                                   cudaMemcpyDeviceToDevice, st));
+                ix->n_local += nb;
+            } else if (ix->shard_count == 1) {
+                RET(ix->dcodes.reserve((size_t)(ix->n_local + nb) * cb, (size_t)ix->n_local * cb, st));
+                CK(cudaMemcpyAsync(ix->dcodes.as<uint8_t>() + ix->n_local * cb, dcodes, (size_t)nb * cb,
+                                   cudaMemcpyDeviceToDevice, st));
+                for (int64_t i = 0; i < nb; ++i) {
+                    ix->h_list.push_back(hl[i]);
+                    ix->h_iid.push_back((int32_t)(ix->n + b + i));
+                }
+                ix->n_local += nb;
+            } else {
+                // keep only the lists this shard owns (l % shard_count == shard_rank), iids stay global
+                hsel.clear();
+                for (int64_t i = 0; i < nb; ++i)
+                    if (hl[i] % ix->shard_count == ix->shard_rank) {
+                        hsel.push_back(i);
+                        ix->h_list.push_back(hl[i]);
+                        ix->h_iid.push_back((int32_t)(ix->n + b + i));
+                    }
+                int64_t ns = (int64_t)hsel.size();
+                if (ns) {
+                    RET(ix->dcodes.reserve((size_t)(ix->n_local + ns) * cb, (size_t)ix->n_local * cb, st));
+                    CK(cudaMemcpyAsync(dsel, hsel.data(), sizeof(int64_t) * (size_t)ns, cudaMemcpyHostToDevice, st));
+                    k_gather_rows<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(dcodes, dsel, ns, cb,
+                                                                                 ix->dcodes.as<uint8_t>() + ix->n_local * cb);
+                    RET(post_launch("k_gather_rows", &launches));
+                    ix->n_local += ns;
+                }
+            }
+            ix->sealed = false;
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+    if (store) ix->n += n;
+    ix->last_launches = launches;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_add(mmidx_t *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes) {
+    return add_or_encode(ix, n, X, out_list, out_codes, true);
+}
+
+extern "C" int mmidx_encode(mmidx_t *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes) {
+    return add_or_encode(ix, n, X, out_list, out_codes, false);
+}
+
+extern "C" int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, const void *codes) {
+    if (!ix || (n > 0 && !codes)) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type == MMIDX_LINEAR) return fail(MMIDX_ERR_INVALID, "Linear index stores vectors, not codes");
+    if (ix->p.type == MMIDX_IVFPQ && n > 0 && !list_ids) return fail(MMIDX_ERR_INVALID, "list_ids required for IVFPQ");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (ix->n + n > ix->p.max_n) return fail(MMIDX_ERR_FULL, "Maximum index capacity reached");
+    const int cb = ix->code_bytes;
+    cudaStream_t st = ix->stream;
+    // validate: code values < ks, list ids in range
+    if (ix->p.ks <= 256) {
+        if (ix->p.ks < 256) {
+            const uint8_t *c = (const uint8_t *)codes;
+            for (int64_t i = 0; i < n * ix->p.m; ++i)
+                if (c[i] >= ix->p.ks) return fail(MMIDX_ERR_INVALID, "code value %d >= ks", (int)c[i]);
+        }
+    } else {
+        const uint16_t *c = (const uint16_t *)codes;
+        for (int64_t i = 0; i < n * ix->p.m; ++i)
+            if (c[i] >= ix->p.ks) return fail(MMIDX_ERR_INVALID, "code value %d >= ks", (int)c[i]);
+    }
+    if (ix->p.type == MMIDX_PQ) {
+        RET(ix->dcodes.reserve((size_t)(ix->n_local + n) * cb, (size_t)ix->n_local * cb, st));
+        CK(cudaMemcpyAsync(ix->dcodes.as<uint8_t>() + ix->n_local * cb, codes, (size_t)n * cb, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        ix->n_local += n;
+        ix->n += n;
+        return MMIDX_OK;
+    }
+    for (int64_t i = 0; i < n; ++i)
+        if (list_ids[i] < 0 || list_ids[i] >= ix->p.nlist) return fail(MMIDX_ERR_INVALID, "list id %d out of range", list_ids[i]);
+    std::vector<uint8_t> sel;
+    const uint8_t *src = (const uint8_t *)codes;
+    int64_t ns = n;
+    if (ix->shard_count > 1) {
+        sel.reserve((size_t)n * cb / ix->shard_count + 64);
+        ns = 0;
+        for (int64_t i = 0; i < n; ++i)
+            if (list_ids[i] % ix->shard_count == ix->shard_rank) {
+                sel.insert(sel.end(), src + i * cb, src + (i + 1) * cb);
+                ix->h_list.push_back(list_ids[i]);
+                ix->h_iid.push_back((int32_t)(ix->n + i));
+                ++ns;
+            }
+        src = sel.data();
+    } else {
+        for (int64_t i = 0; i < n; ++i) {
+            ix->h_list.push_back(list_ids[i]);
+            ix->h_iid.push_back((int32_t)(ix->n + i));
+        }
+    }
+    if (ns) {
+        RET(ix->dcodes.reserve((size_t)(ix->n_local + ns) * cb, (size_t)ix->n_local * cb, st));
+        CK(cudaMemcpyAsync(ix->dcodes.as<uint8_t>() + ix->n_local * cb, src, (size_t)ns * cb, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    ix->n_local += ns;
+    ix->n += n;
+    ix->sealed = false;
+    return MMIDX_OK;
+}
+
+// group the append log by list (stable => insertion order inside a list, IVFPQ.java:337-346)
+static int seal(mmidx_index *ix) {
+    if (ix->sealed) return MMIDX_OK;
+    cudaStream_t st = ix->stream;
+    const int nlist = ix->p.nlist, cb = ix->code_bytes;
+    const int64_t nl = ix->n_local;
+    std::fill(ix->h_list_len.begin(), ix->h_list_len.end(), 0);
+    for (int64_t i = 0; i < nl; ++i) ix->h_list_len[ix->h_list[i]]++;
+    int64_t pos = 0;
+    for (int l = 0; l < nlist; ++l) {
+        ix->h_list_off[l] = pos;
+        pos += (ix->h_list_len[l] + 15) & ~15;  // 16-entry aligned starts: 128-bit loads for any code width
+    }
+    const int64_t total = std::max<int64_t>(pos, 16);
+    std::vector<int64_t> dst(nl), cur(ix->h_list_off);
+    for (int64_t i = 0; i < nl; ++i) dst[i] = cur[ix->h_list[i]]++;
+    RET(ix->csr_codes.reserve((size_t)total * cb, 0, st));
+    RET(ix->csr_iids.reserve((size_t)total * sizeof(int32_t), 0, st));
+    RET(ix->dlist_off.reserve(sizeof(int64_t) * (size_t)nlist, 0, st));
+    RET(ix->dlist_len.reserve(sizeof(int32_t) * (size_t)nlist, 0, st));
+    CK(cudaMemsetAsync(ix->csr_codes.p, 0, (size_t)total * cb, st));
+    CK(cudaMemsetAsync(ix->csr_iids.p, 0xff, (size_t)total * sizeof(int32_t), st));
+    CK(cudaMemcpyAsync(ix->dlist_off.p, ix->h_list_off.data(), sizeof(int64_t) * (size_t)nlist, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ix->dlist_len.p, ix->h_list_len.data(), sizeof(int32_t) * (size_t)nlist, cudaMemcpyHostToDevice, st));
+    if (nl) {
+        Scratch sc(st);
+        int64_t *ddst;
+        int32_t *diid;
+        RET(sc.get(&ddst, (size_t)nl));
+        RET(sc.get(&diid, (size_t)nl));
+        CK(cudaMemcpyAsync(ddst, dst.data(), sizeof(int64_t) * (size_t)nl, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(diid, ix->h_iid.data(), sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, st));
+        k_scatter_codes<<<(unsigned)((nl + 255) / 256), 256, 0, st>>>(ix->dcodes.as<uint8_t>(), diid, ddst, nl, cb,
+                                                                     ix->csr_codes.as<uint8_t>(), ix->csr_iids.as<int32_t>());
+        RET(post_launch("k_scatter_codes", nullptr));
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaStreamSynchronize(st));
+    ix->sealed = true;
+    return MMIDX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------------------
+static inline int cap_for(int k) { return k <= 512 ? 1024 : 2048; }
+
+template <int CAP>
+static size_t topk_bytes() {
+    return (sizeof(TopK<CAP>) + 127) & ~(size_t)127;
+}
+
+struct StageMark {
+    mmidx_index *ix;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr;
+    int stage;
+    StageMark(mmidx_index *i, cudaStream_t s, int stg) : ix(i), st(s), stage(stg) {
+        if (ix->timer.enabled) {
+            a = ix->timer.get();
+            cudaEventRecord(a, st);
+        }
+    }
+    void end() {
+        if (a) {
+            cudaEvent_t b = ix->timer.get();
+            cudaEventRecord(b, st);
+            ix->timer.spans.push_back({a, b, stage});
+            a = nullptr;
+        }
+    }
+    ~StageMark() { end(); }
+};
+
+// coarse stage for a chunk: D (scratch) and probes[nq][w] in queue order
+static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w, int32_t *dprobes, Scratch &sc,
+                            cudaStream_t st, int *launches) {
+    const int nlist = ix->p.nlist, d = ix->p.d;
+    double *D, *pd;
+    int32_t *pcnt, *amb_list, *amb_count;
+    RET(sc.get(&D, (size_t)nq * nlist));
+    RET(sc.get(&pd, (size_t)nq * w));
+    RET(sc.get(&pcnt, (size_t)nq));
+    RET(sc.get(&amb_list, (size_t)nq));
+    RET(sc.get(&amb_count, 1));
+    CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+    dim3 g1((unsigned)((nlist + MMIDX_NT - 1) / MMIDX_NT), (unsigned)((nq + QT - 1) / QT));
+    k_sqdist_matrix<<<g1, MMIDX_NT, 0, st>>>(dQ, ix->dCt.as<double>(), nq, nlist, d, D);
+    RET(post_launch("k_sqdist_matrix", launches));
+    TopkOut o{};
+    o.iids = dprobes;
+    o.dist = pd;
+    o.seq = nullptr;
+    o.cnt = pcnt;
+    o.tie = nullptr;
+    o.amb_list = amb_list;
+    o.amb_count = amb_count;
+    o.nparts = 1;
+    if (cap_for(w) == 1024) {
+        size_t smem = topk_bytes<1024>();
+        RET(set_smem(k_select_rows<1024>, smem));
+        k_select_rows<1024><<<(unsigned)nq, MMIDX_NT, smem, st>>>(D, nlist, w, o);
+    } else {
+        size_t smem = topk_bytes<2048>();
+        RET(set_smem(k_select_rows<2048>, smem));
+        k_select_rows<2048><<<(unsigned)nq, MMIDX_NT, smem, st>>>(D, nlist, w, o);
+    }
+    RET(post_launch("k_select_rows", launches));
+    // ordered tie pass for rows whose w-th boundary was an exact tie
+    TieLists tl;
+    RET(sc.get(&tl.seq, (size_t)nq * w));
+    RET(sc.get(&tl.pay, (size_t)nq * w));
+    RET(sc.get(&tl.eq, (size_t)nq * w));
+    RET(sc.get(&tl.cnt, (size_t)nq));
+    const int tg = (int)std::min<int64_t>(nq, 296);
+    k_tie_collect_rows<<<tg, MMIDX_NT, 0, st>>>(D, nlist, w, pd, amb_list, amb_count, tl);
+    RET(post_launch("k_tie_collect_rows", launches));
+    size_t fs = (size_t)w * 16;
+    RET(set_smem(k_tie_finish, std::max<size_t>(fs, 1024 * 16)));
+    k_tie_finish<<<tg, MMIDX_NT, fs, st>>>(1, nq, w, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, dprobes, pd, nullptr);
+    RET(post_launch("k_tie_finish", launches));
+    return MMIDX_OK;
+}
+
+static inline int64_t lut_stride_of(const mmidx_index *ix) { return ((int64_t)ix->p.m * ix->p.ks + 1) & ~(int64_t)1; }
+
+static int launch_lut(mmidx_index *ix, const double *dQ, const int32_t *dprobes, int64_t npairs, int w, double *dlut,
+                      cudaStream_t st, int *launches) {
+    if (npairs == 0) return MMIDX_OK;
+    const int S = ix->S, m = ix->p.m, ks = ix->p.ks, d = ix->p.d;
+    const int32_t *perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
+    const double *C = dprobes ? ix->dC.as<double>() : nullptr;
+    dim3 grid((unsigned)((npairs + LUT_PT - 1) / LUT_PT), m);
+    size_t smem = (size_t)LUT_PT * S * sizeof(double);
+#define LUTK(SV)                                                                                                       \
+    case SV:                                                                                                           \
+        k_lut_build<SV><<<grid, MMIDX_NT, smem, st>>>(dQ, C, dprobes, perm, ix->dP.as<double>(), npairs, w, d, m, ks, S, lut_stride_of(ix), dlut); \
+        break;
+    switch (S) {
+        LUTK(2) LUTK(4) LUTK(8) LUTK(16) LUTK(32)
+        default:
+            if (smem > 48 * 1024) RET(set_smem(k_lut_build<0>, smem));
+            k_lut_build<0><<<grid, MMIDX_NT, smem, st>>>(dQ, C, dprobes, perm, ix->dP.as<double>(), npairs, w, d, m, ks, S, lut_stride_of(ix), dlut);
+    }
+#undef LUTK
+    return post_launch("k_lut_build", launches);
+}
+
+struct ResultBufs {
+    int32_t *iids;
+    double *dist;
+    unsigned long long *seq;  // may be NULL
+    int32_t *cnt;
+};
+
+// merge [nq][nparts][k] partial results into res, flagging ambiguous queries
+template <int CAP>
+static int launch_merge(const TopkOut &part, int nparts, int64_t nq, int k, const ResultBufs &res, int32_t *amb_list,
+                        int32_t *amb_count, double *out_tie, int64_t part_stride, int64_t q_stride, cudaStream_t st,
+                        int *launches) {
+    MergeArgs a{};
+    a.iids = part.iids;
+    a.dist = part.dist;
+    a.seq = part.seq;
+    a.cnt = part.cnt;
+    a.tie = part.tie;
+    a.part_stride = part_stride;
+    a.q_stride = q_stride;
+    a.nparts = nparts;
+    a.k = k;
+    TopkOut o{};
+    o.iids = res.iids;
+    o.dist = res.dist;
+    o.seq = res.seq;
+    o.cnt = res.cnt;
+    o.tie = out_tie;
+    o.amb_list = amb_list;
+    o.amb_count = amb_count;
+    o.nparts = 1;
+    size_t smem = topk_bytes<CAP>();
+    RET(set_smem(k_merge_topk<CAP>, smem));
+    k_merge_topk<CAP><<<(unsigned)nq, MMIDX_NT, smem, st>>>(a, o);
+    return post_launch("k_merge_topk", launches);
+}
+
+static int smem_limit_for_luts() { return 200 * 1024; }
+
+// one chunk of IVFPQ queries.  want_seq: keep offer sequence numbers (sharded search).
+// local_only_ties: true on a sharded index (ties are resolved after the cross-shard merge instead).
+template <int CAP>
+static int ivfpq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, int w, const ResultBufs &res,
+                       double *res_tie, int32_t *amb_list, int32_t *amb_count, bool resolve_ties, cudaStream_t st,
+                       int *launches) {
+    Scratch sc(st);
+    const int m = ix->p.m, ks = ix->p.ks;
+    int32_t *dprobes;
+    double *dlut;
+    RET(sc.get(&dprobes, (size_t)nq * w));
+    RET(sc.get(&dlut, (size_t)nq * w * lut_stride_of(ix)));
+    {
+        StageMark sm(ix, st, 0);
+        RET(coarse_probe_dev(ix, dQ, nq, w, dprobes, sc, st, launches));
+    }
+    {
+        StageMark sm(ix, st, 1);
+        RET(launch_lut(ix, dQ, dprobes, nq * w, w, dlut, st, launches));
+    }
+    IvfScanArgs a{};
+    a.probes = dprobes;
+    a.luts = dlut;
+    a.lut_stride = lut_stride_of(ix);
+    a.codes = ix->csr_codes.as<uint8_t>();
+    a.iids = ix->csr_iids.as<int32_t>();
+    a.list_off = ix->dlist_off.as<int64_t>();
+    a.list_len = ix->dlist_len.as<int32_t>();
+    a.w = w;
+    a.k = k;
+    a.L.m = m;
+    a.L.ks = ks;
+    a.L.code_bytes = ix->code_bytes;
+    // enough CTAs to fill the machine: split a query's probes over `nsplit` CTAs when the chunk is small
+    int nsplit = (int)std::min<int64_t>(w, std::max<int64_t>(1, (148 * 4 + nq - 1) / nq));
+    a.nsplit = nsplit;
+    const size_t lut_bytes = (size_t)lut_stride_of(ix) * sizeof(double);
+    const size_t smem = topk_bytes<CAP>() + 2 * lut_bytes + 64;
+    if (smem > (size_t)smem_limit_for_luts())
+        return fail(MMIDX_ERR_UNSUPPORTED, "m*ks = %d: ADC table (%zu bytes) does not fit shared memory", m * ks, lut_bytes);
+    RET(set_smem(k_ivfpq_scan<CAP>, smem));
+    TopkOut o{};
+    o.nparts = nsplit;
+    unsigned long long *pseq = nullptr;
+    if (nsplit == 1) {
+        o.iids = res.iids;
+        o.dist = res.dist;
+        o.seq = res.seq;
+        o.cnt = res.cnt;
+        o.tie = res_tie;
+        o.amb_list = amb_list;
+        o.amb_count = amb_count;
+    } else {
+        RET(sc.get(&o.iids, (size_t)nq * nsplit * k));
+        RET(sc.get(&o.dist, (size_t)nq * nsplit * k));
+        RET(sc.get(&pseq, (size_t)nq * nsplit * k));
+        o.seq = pseq;
+        RET(sc.get(&o.cnt, (size_t)nq * nsplit));
+        RET(sc.get(&o.tie, (size_t)nq * nsplit));
+        o.amb_list = nullptr;
+        o.amb_count = nullptr;
+    }
+    {
+        StageMark sm(ix, st, 2);
+        k_ivfpq_scan<CAP><<<dim3(nsplit, (unsigned)nq), MMIDX_NT, smem, st>>>(a, o);
+        RET(post_launch("k_ivfpq_scan", launches));
+    }
+    StageMark sm3(ix, st, 3);
+    if (nsplit > 1)
+        RET(launch_merge<CAP>(o, nsplit, nq, k, res, amb_list, amb_count, res_tie, 1, nsplit, st, launches));
+    if (resolve_ties) {
+        TieLists tl;
+        RET(sc.get(&tl.seq, (size_t)nq * k));
+        RET(sc.get(&tl.pay, (size_t)nq * k));
+        RET(sc.get(&tl.eq, (size_t)nq * k));
+        RET(sc.get(&tl.cnt, (size_t)nq));
+        TieCodeArgs t{};
+        t.luts = dlut;
+    t.lut_stride = lut_stride_of(ix);
+        t.codes = a.codes;
+        t.iids = a.iids;
+        t.probes = dprobes;
+        t.list_off = a.list_off;
+        t.list_len = a.list_len;
+        t.w = w;
+        t.m = m;
+        t.ks = ks;
+        t.code_bytes = ix->code_bytes;
+        t.k = k;
+        const int tg = (int)std::min<int64_t>(nq, 296);
+        k_tie_collect_ivfpq<<<tg, MMIDX_NT, 0, st>>>(t, res.dist, amb_list, amb_count, tl);
+        RET(post_launch("k_tie_collect_ivfpq", launches));
+        k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count,
+                                                           res.iids, res.dist, res.seq);
+        RET(post_launch("k_tie_finish", launches));
+    }
+    return MMIDX_OK;
+}
+
+template <int CAP>
+static int pq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, const ResultBufs &res, int32_t *amb_list,
+                    int32_t *amb_count, cudaStream_t st, int *launches) {
+    Scratch sc(st);
+    const int m = ix->p.m, ks = ix->p.ks;
+    double *dlut;
+    RET(sc.get(&dlut, (size_t)nq * lut_stride_of(ix)));
+    {
+        StageMark sm(ix, st, 1);
+        RET(launch_lut(ix, dQ, nullptr, nq, 1, dlut, st, launches));
+    }
+    constexpr int ROUND = TopK<CAP>::ROUND;
+    const int64_t n = ix->n_local;
+    int64_t rounds = std::max<int64_t>(1, (n + ROUND - 1) / ROUND);
+    int64_t want = std::max<int64_t>(1, (148 * 4 + nq - 1) / nq);
+    int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(want, rounds));
+    int64_t chunk = ((rounds + nsplit - 1) / nsplit) * ROUND;
+    nsplit = (int)std::max<int64_t>(1, (n + chunk - 1) / chunk);
+    PqScanArgs a{};
+    a.luts = dlut;
+    a.lut_stride = lut_stride_of(ix);
+    a.codes = ix->dcodes.as<uint8_t>();
+    a.n = n;
+    a.chunk = chunk;
+    a.k = k;
+    a.L.m = m;
+    a.L.ks = ks;
+    a.L.code_bytes = ix->code_bytes;
+    const size_t lut_bytes = (size_t)lut_stride_of(ix) * sizeof(double);
+    const size_t smem = topk_bytes<CAP>() + lut_bytes + 64;
+    if (smem > (size_t)smem_limit_for_luts())
+        return fail(MMIDX_ERR_UNSUPPORTED, "m*ks = %d: ADC table (%zu bytes) does not fit shared memory", m * ks, lut_bytes);
+    RET(set_smem(k_pq_scan<CAP>, smem));
+    TopkOut o{};
+    o.nparts = nsplit;
+    if (nsplit == 1) {
+        o.iids = res.iids;
+        o.dist = res.dist;
+        o.seq = res.seq;
+        o.cnt = res.cnt;
+        o.tie = nullptr;
+        o.amb_list = amb_list;
+        o.amb_count = amb_count;
+    } else {
+        unsigned long long *pseq;
+        RET(sc.get(&o.iids, (size_t)nq * nsplit * k));
+        RET(sc.get(&o.dist, (size_t)nq * nsplit * k));
+        RET(sc.get(&pseq, (size_t)nq * nsplit * k));
+        o.seq = pseq;
+        RET(sc.get(&o.cnt, (size_t)nq * nsplit));
+        RET(sc.get(&o.tie, (size_t)nq * nsplit));
+    }
+    {
+        StageMark sm(ix, st, 2);
+        k_pq_scan<CAP><<<dim3(nsplit, (unsigned)nq), MMIDX_NT, smem, st>>>(a, o);
+        RET(post_launch("k_pq_scan", launches));
+    }
+    StageMark sm3(ix, st, 3);
+    if (nsplit > 1)
+        RET(launch_merge<CAP>(o, nsplit, nq, k, res, amb_list, amb_count, nullptr, 1, nsplit, st, launches));
+    TieLists tl;
+    RET(sc.get(&tl.seq, (size_t)nq * k));
+    RET(sc.get(&tl.pay, (size_t)nq * k));
+    RET(sc.get(&tl.eq, (size_t)nq * k));
+    RET(sc.get(&tl.cnt, (size_t)nq));
+    TieCodeArgs t{};
+    t.luts = dlut;
+    t.lut_stride = lut_stride_of(ix);
+    t.codes = a.codes;
+    t.n = n;
+    t.w = 1;
+    t.m = m;
+    t.ks = ks;
+    t.code_bytes = ix->code_bytes;
+    t.k = k;
+    const int tg = (int)std::min<int64_t>(nq, 296);
+    k_tie_collect_pq<<<tg, MMIDX_NT, 0, st>>>(t, res.dist, amb_list, amb_count, tl);
+    RET(post_launch("k_tie_collect_pq", launches));
+    k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, res.iids,
+                                                       res.dist, res.seq);
+    RET(post_launch("k_tie_finish", launches));
+    return MMIDX_OK;
+}
+
+template <int CAP>
+static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, const ResultBufs &res, int32_t *amb_list,
+                        int32_t *amb_count, cudaStream_t st, int *launches) {
+    Scratch sc(st);
+    constexpr int ROUND = TopK<CAP>::ROUND;
+    const int64_t n = ix->n_local;
+    const int d = ix->p.d;
+    int64_t rounds = std::max<int64_t>(1, (n + ROUND - 1) / ROUND);
+    int64_t want = std::max<int64_t>(1, (148 * 4 + nq - 1) / nq);
+    int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(want, rounds));
+    int64_t chunk = ((rounds + nsplit - 1) / nsplit) * ROUND;
+    nsplit = (int)std::max<int64_t>(1, (n + chunk - 1) / chunk);
+    LinearArgs a{};
+    a.Q = dQ;
+    a.Xb = ix->dXb.as<double>();
+    a.n = n;
+    a.chunk = chunk;
+    a.d = d;
+    a.k = k;
+    const size_t smem = topk_bytes<CAP>() + (size_t)d * sizeof(double) + 64;
+    RET(set_smem(k_linear_scan<CAP>, smem));
+    TopkOut o{};
+    o.nparts = nsplit;
+    if (nsplit == 1) {
+        o.iids = res.iids;
+        o.dist = res.dist;
+        o.seq = res.seq;
+        o.cnt = res.cnt;
+        o.tie = nullptr;
+        o.amb_list = amb_list;
+        o.amb_count = amb_count;
+    } else {
+        unsigned long long *pseq;
+        RET(sc.get(&o.iids, (size_t)nq * nsplit * k));
+        RET(sc.get(&o.dist, (size_t)nq * nsplit * k));
+        RET(sc.get(&pseq, (size_t)nq * nsplit * k));
+        o.seq = pseq;
+        RET(sc.get(&o.cnt, (size_t)nq * nsplit));
+        RET(sc.get(&o.tie, (size_t)nq * nsplit));
+    }
+    {
+        StageMark sm(ix, st, 2);
+        k_linear_scan<CAP><<<dim3(nsplit, (unsigned)nq), MMIDX_NT, smem, st>>>(a, o);
+        RET(post_launch("k_linear_scan", launches));
+    }
+    StageMark sm3(ix, st, 3);
+    if (nsplit > 1)
+        RET(launch_merge<CAP>(o, nsplit, nq, k, res, amb_list, amb_count, nullptr, 1, nsplit, st, launches));
+    TieLists tl;
+    RET(sc.get(&tl.seq, (size_t)nq * k));
+    RET(sc.get(&tl.pay, (size_t)nq * k));
+    RET(sc.get(&tl.eq, (size_t)nq * k));
+    RET(sc.get(&tl.cnt, (size_t)nq));
+    const int tg = (int)std::min<int64_t>(nq, 296);
+    k_tie_collect_linear<<<tg, MMIDX_NT, 0, st>>>(dQ, a.Xb, n, d, k, res.dist, amb_list, amb_count, tl);
+    RET(post_launch("k_tie_collect_linear", launches));
+    k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, res.iids,
+                                                       res.dist, res.seq);
+    RET(post_launch("k_tie_finish", launches));
+    return MMIDX_OK;
+}
+
+static int validate_search(mmidx_index *ix, int64_t nq, int k, int *w_out) {
+    if (nq < 0) return fail(MMIDX_ERR_INVALID, "nq < 0");
+    if (k < 1) return fail(MMIDX_ERR_INVALID, "k must be >= 1 (BoundedPriorityQueue max size)");
+    if (k > MMIDX_MAX_K) return fail(MMIDX_ERR_UNSUPPORTED, "k = %d exceeds MMIDX_MAX_K = %d", k, MMIDX_MAX_K);
+    RET(require_quantizers(ix));
+    if (ix->p.type == MMIDX_IVFPQ) {
+        int w = ix->p.w;
+        if (w < 1) return fail(MMIDX_ERR_W, "w = %d: BoundedPriorityQueue needs a positive size", w);
+        if (w > ix->p.nlist) return fail(MMIDX_ERR_W, "w = %d exceeds the number of coarse centroids %d", w, ix->p.nlist);
+        if (w > MMIDX_MAX_K) return fail(MMIDX_ERR_UNSUPPORTED, "w = %d exceeds %d", w, MMIDX_MAX_K);
+        *w_out = w;
+    }
+    return MMIDX_OK;
+}
+
+// device-side search over all chunks.  d_seq/d_tie non-NULL => sharded mode (no local tie resolution).
+static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k, int32_t *d_iids, double *d_dist,
+                           unsigned long long *d_seq, double *d_tie, int32_t *d_count, cudaStream_t st, bool sharded) {
+    int w = 0;
+    RET(validate_search(ix, nq, k, &w));
+    if (nq == 0) return MMIDX_OK;
+    if (ix->p.type == MMIDX_IVFPQ && !ix->sealed) {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        RET(seal(ix));
+    }
+    int launches = 0;
+    ix->timer.reset();
+    StageMark whole(ix, st, 4);
+    Scratch sc(st);
+    int32_t *amb_list, *amb_count;
+    const int d = ix->p.d;
+    int64_t qchunk = nq;
+    if (ix->p.type == MMIDX_IVFPQ) {
+        size_t per_q = (size_t)w * ix->p.m * ix->p.ks * sizeof(double);
+        qchunk = std::max<int64_t>(1, (int64_t)(ix->lut_chunk_bytes / per_q));
+    } else if (ix->p.type == MMIDX_PQ) {
+        size_t per_q = (size_t)ix->p.m * ix->p.ks * sizeof(double);
+        qchunk = std::max<int64_t>(1, (int64_t)(((size_t)256 << 20) / per_q));
+    } else {
+        qchunk = 16384;
+    }
+    qchunk = std::min<int64_t>(qchunk, 32768);  // grid.y limit is 65535
+    qchunk = std::min(qchunk, nq);
+    RET(sc.get(&amb_list, (size_t)qchunk));
+    RET(sc.get(&amb_count, 1));
+    for (int64_t q0 = 0; q0 < nq; q0 += qchunk) {
+        int64_t nb = std::min(qchunk, nq - q0);
+        CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+        ResultBufs res{d_iids + q0 * k, d_dist + q0 * k, d_seq ? d_seq + q0 * k : nullptr, d_count + q0};
+        const double *dq = dQ + q0 * d;
+        int r;
+        const bool big = cap_for(k) == 2048;
+        switch (ix->p.type) {
+            case MMIDX_IVFPQ:
+                r = big ? ivfpq_chunk<2048>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches)
+                        : ivfpq_chunk<1024>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches);
+                break;
+            case MMIDX_PQ:
+                r = big ? pq_chunk<2048>(ix, dq, nb, k, res, amb_list, amb_count, st, &launches)
+                        : pq_chunk<1024>(ix, dq, nb, k, res, amb_list, amb_count, st, &launches);
+                break;
+            default:
+                r = big ? linear_chunk<2048>(ix, dq, nb, k, res, amb_list, amb_count, st, &launches)
+                        : linear_chunk<1024>(ix, dq, nb, k, res, amb_list, amb_count, st, &launches);
+        }
+        RET(r);
+    }
+    whole.end();
+    ix->last_launches = launches;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_search_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, int32_t *d_iids, double *d_dist,
+                                int32_t *d_count, void *stream) {
+    if (!ix || (nq > 0 && (!dQ || !d_iids || !d_dist || !d_count))) return fail(MMIDX_ERR_INVALID, "null argument");
+    DeviceGuard g(ix->device);
+    if (ix->shard_count > 1)
+        return fail(MMIDX_ERR_STATE, "sharded index: use mmidx_search_shard_dev + mmidx_merge_topk_dev");
+    return search_dev_impl(ix, nq, dQ, k, d_iids, d_dist, nullptr, nullptr, d_count, (cudaStream_t)stream, false);
+}
+
+extern "C" int mmidx_search_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, int32_t *d_iids, double *d_dist,
+                                      int64_t *d_seq, double *d_tie, int32_t *d_count, void *stream) {
+    if (!ix || (nq > 0 && (!dQ || !d_iids || !d_dist || !d_seq || !d_tie || !d_count)))
+        return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "sharded search is defined for IVFPQ");
+    DeviceGuard g(ix->device);
+    return search_dev_impl(ix, nq, dQ, k, d_iids, d_dist, (unsigned long long *)d_seq, d_tie, d_count, (cudaStream_t)stream, true);
+}
+
+extern "C" int mmidx_merge_topk_dev(int64_t nq, int32_t k, int32_t nparts, const int32_t *d_iids, const double *d_dist,
+                                    const int64_t *d_seq, const double *d_tie, const int32_t *d_count, int32_t *d_out_iids,
+                                    double *d_out_dist, int64_t *d_out_seq, int32_t *d_out_count, int32_t *d_amb_list,
+                                    int32_t *d_amb_count, void *stream) {
+    if (nq < 0 || k < 1 || k > MMIDX_MAX_K || nparts < 1) return fail(MMIDX_ERR_INVALID, "bad merge geometry");
+    if (nq == 0) return MMIDX_OK;
+    if (!d_iids || !d_dist || !d_seq || !d_count || !d_out_iids || !d_out_dist || !d_out_count || !d_amb_list || !d_amb_count)
+        return fail(MMIDX_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(d_amb_count, 0, sizeof(int32_t), st));
+    TopkOut part{};
+    part.iids = const_cast<int32_t *>(d_iids);
+    part.dist = const_cast<double *>(d_dist);
+    part.seq = (unsigned long long *)const_cast<int64_t *>(d_seq);
+    part.cnt = const_cast<int32_t *>(d_count);
+    part.tie = const_cast<double *>(d_tie);
+    ResultBufs res{d_out_iids, d_out_dist, (unsigned long long *)d_out_seq, d_out_count};
+    int launches = 0;
+    // all-gather layout [nparts][nq][k]: row(part, q) = part*nq + q
+    if (nq > 32768) return fail(MMIDX_ERR_UNSUPPORTED, "merge handles at most 32768 queries per call");
+    if (cap_for(k) == 2048)
+        RET(launch_merge<2048>(part, nparts, nq, k, res, d_amb_list, d_amb_count, nullptr, nq, 1, st, &launches));
+    else
+        RET(launch_merge<1024>(part, nparts, nq, k, res, d_amb_list, d_amb_count, nullptr, nq, 1, st, &launches));
+    return MMIDX_OK;
+}
+
+// sharded tie pass, step 1 (per shard): first-k entries in offer order with dist <= T of every ambiguous query.
+// T is read from the merged result d_res_dist[q][k-1].  Needs the LUTs again, so it re-runs coarse + LUT for
+// the ambiguous queries only (rare path).
+extern "C" int mmidx_tie_collect_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, const double *d_res_dist,
+                                           const int32_t *d_amb_list, const int32_t *d_amb_count, int64_t *d_l_seq,
+                                           int32_t *d_l_iid, int32_t *d_l_eq, int32_t *d_l_cnt, void *stream) {
+    if (!ix || !dQ || !d_res_dist || !d_amb_list || !d_amb_count || !d_l_seq || !d_l_iid || !d_l_eq || !d_l_cnt)
+        return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "sharded search is defined for IVFPQ");
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int w = 0;
+    RET(validate_search(ix, nq, k, &w));
+    // host needs the ambiguous count to size the recomputation
+    int32_t na = 0;
+    CK(cudaMemcpyAsync(&na, d_amb_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemsetAsync(d_l_cnt, 0, sizeof(int32_t) * (size_t)nq, st));
+    if (na == 0) return MMIDX_OK;
+    std::vector<int32_t> amb(na);
+    CK(cudaMemcpyAsync(amb.data(), d_amb_list, sizeof(int32_t) * (size_t)na, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int launches = 0;
+    const int m = ix->p.m, ks = ix->p.ks, d = ix->p.d;
+    // process ambiguous queries in small groups: gather their vectors, rebuild probes + LUTs, collect
+    const int64_t G = std::max<int64_t>(1, (int64_t)(ix->lut_chunk_bytes / ((size_t)w * m * ks * sizeof(double))));
+    for (int64_t a0 = 0; a0 < na; a0 += G) {
+        int64_t nb = std::min<int64_t>(G, na - a0);
+        Scratch sc(st);
+        double *gQ, *dlut, *gT;
+        int32_t *dprobes, *gl, *gcount;
+        int64_t *gidx;
+        RET(sc.get(&gQ, (size_t)nb * d));
+        RET(sc.get(&dlut, (size_t)nb * w * lut_stride_of(ix)));
+        RET(sc.get(&dprobes, (size_t)nb * w));
+        RET(sc.get(&gidx, (size_t)nb));
+        RET(sc.get(&gT, (size_t)nb * k));
+        RET(sc.get(&gl, (size_t)nb));
+        RET(sc.get(&gcount, 1));
+        std::vector<int64_t> hidx(nb);
+        std::vector<int32_t> hl(nb);
+        for (int64_t i = 0; i < nb; ++i) {
+            hidx[i] = amb[a0 + i];
+            hl[i] = (int32_t)i;
+        }
+        int32_t nb32 = (int32_t)nb;
+        CK(cudaMemcpyAsync(gidx, hidx.data(), sizeof(int64_t) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(gl, hl.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(gcount, &nb32, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        k_gather_rows<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((const uint8_t *)dQ, gidx, nb, d * (int)sizeof(double), (uint8_t *)gQ);
+        RET(post_launch("k_gather_rows", &launches));
+        k_gather_rows<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((const uint8_t *)d_res_dist, gidx, nb, k * (int)sizeof(double), (uint8_t *)gT);
+        RET(post_launch("k_gather_rows", &launches));
+        RET(coarse_probe_dev(ix, gQ, nb, w, dprobes, sc, st, &launches));
+        RET(launch_lut(ix, gQ, dprobes, nb * w, w, dlut, st, &launches));
+        TieLists tl;
+        RET(sc.get(&tl.seq, (size_t)nb * k));
+        RET(sc.get(&tl.pay, (size_t)nb * k));
+        RET(sc.get(&tl.eq, (size_t)nb * k));
+        RET(sc.get(&tl.cnt, (size_t)nb));
+        TieCodeArgs t{};
+        t.luts = dlut;
+    t.lut_stride = lut_stride_of(ix);
+        t.codes = ix->csr_codes.as<uint8_t>();
+        t.iids = ix->csr_iids.as<int32_t>();
+        t.probes = dprobes;
+        t.list_off = ix->dlist_off.as<int64_t>();
+        t.list_len = ix->dlist_len.as<int32_t>();
+        t.w = w;
+        t.m = m;
+        t.ks = ks;
+        t.code_bytes = ix->code_bytes;
+        t.k = k;
+        k_tie_collect_ivfpq<<<(unsigned)std::min<int64_t>(nb, 296), MMIDX_NT, 0, st>>>(t, gT, gl, gcount, tl);
+        RET(post_launch("k_tie_collect_ivfpq", &launches));
+        // scatter the group's lists back to rows indexed by the original query id
+        for (int64_t i = 0; i < nb; ++i) {
+            int64_t q = hidx[i];
+            CK(cudaMemcpyAsync(d_l_seq + q * k, tl.seq + i * k, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(d_l_iid + q * k, tl.pay + i * k, sizeof(int32_t) * (size_t)k, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(d_l_eq + q * k, tl.eq + i * k, sizeof(int32_t) * (size_t)k, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(d_l_cnt + q, tl.cnt + i, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+    return MMIDX_OK;
+}
+
+// sharded tie pass, step 2 (after all-gathering the lists): patch the merged result in place
+extern "C" int mmidx_tie_finish_dev(int64_t nq, int32_t k, int32_t nparts, const int64_t *d_l_seq, const int32_t *d_l_iid,
+                                    const int32_t *d_l_eq, const int32_t *d_l_cnt, const int32_t *d_amb_list,
+                                    const int32_t *d_amb_count, int32_t *d_res_iids, double *d_res_dist, void *stream) {
+    if (nq <= 0) return MMIDX_OK;
+    if (k < 1 || k > MMIDX_MAX_K || nparts < 1) return fail(MMIDX_ERR_INVALID, "bad geometry");
+    cudaStream_t st = (cudaStream_t)stream;
+    RET(set_smem(k_tie_finish, (size_t)1024 * 16));
+    k_tie_finish<<<(unsigned)std::min<int64_t>(nq, 296), MMIDX_NT, (size_t)k * 16, st>>>(
+        nparts, nq, k, (const unsigned long long *)d_l_seq, d_l_iid, d_l_eq, d_l_cnt, d_amb_list, d_amb_count, d_res_iids,
+        d_res_dist, nullptr);
+    return post_launch("k_tie_finish", nullptr);
+}
+
+extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k, int32_t *out_iids, double *out_dist,
+                            int32_t *out_count) {
+    if (!ix || (nq > 0 && (!Q || !out_iids || !out_dist))) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->shard_count > 1) return fail(MMIDX_ERR_STATE, "sharded index: use the *_shard_dev entry points");
+    int w = 0;
+    RET(validate_search(ix, nq, k, &w));
+    if (nq == 0) return MMIDX_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    Scratch sc(st);
+    double *dQ, *ddist;
+    int32_t *diids, *dcnt;
+    RET(sc.get(&dQ, (size_t)nq * ix->p.d));
+    RET(sc.get(&ddist, (size_t)nq * k));
+    RET(sc.get(&diids, (size_t)nq * k));
+    RET(sc.get(&dcnt, (size_t)nq));
+    CK(cudaMemcpyAsync(dQ, Q, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
+    RET(search_dev_impl(ix, nq, dQ, k, diids, ddist, nullptr, nullptr, dcnt, st, false));
+    CK(cudaMemcpyAsync(out_iids, diids, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_dist, ddist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    if (out_count) CK(cudaMemcpyAsync(out_count, dcnt, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_coarse_probe(mmidx_t *ix, int64_t nq, const double *Q, int32_t w, int32_t *out) {
+    if (!ix || (nq > 0 && (!Q || !out))) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "coarse probe applies to IVFPQ only");
+    if (!ix->has_C) return fail(MMIDX_ERR_STATE, "coarse quantizer not loaded");
+    if (w < 1 || w > ix->p.nlist) return fail(MMIDX_ERR_W, "w = %d out of 1..nlist", w);
+    if (w > MMIDX_MAX_K) return fail(MMIDX_ERR_UNSUPPORTED, "w = %d exceeds %d", w, MMIDX_MAX_K);
+    if (nq == 0) return MMIDX_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    int launches = 0;
+    const int64_t QC = 8192;
+    for (int64_t q0 = 0; q0 < nq; q0 += QC) {
+        int64_t nb = std::min(QC, nq - q0);
+        Scratch sc(st);
+        double *dQ;
+        int32_t *dpr;
+        RET(sc.get(&dQ, (size_t)nb * ix->p.d));
+        RET(sc.get(&dpr, (size_t)nb * w));
+        CK(cudaMemcpyAsync(dQ, Q + q0 * ix->p.d, sizeof(double) * (size_t)nb * ix->p.d, cudaMemcpyHostToDevice, st));
+        RET(coarse_probe_dev(ix, dQ, nb, w, dpr, sc, st, &launches));
+        CK(cudaMemcpyAsync(out + q0 * w, dpr, sizeof(int32_t) * (size_t)nb * w, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    ix->last_launches = launches;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_pq_lut(mmidx_t *ix, int64_t nq, const double *V, double *out) {
+    if (!ix || (nq > 0 && (!V || !out))) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type == MMIDX_LINEAR) return fail(MMIDX_ERR_INVALID, "Linear index has no ADC table");
+    if (!ix->has_P) return fail(MMIDX_ERR_STATE, "product quantizer not loaded");
+    if (nq == 0) return MMIDX_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    Scratch sc(st);
+    double *dV, *dl;
+    const size_t row = (size_t)ix->p.m * ix->p.ks, stride = (size_t)lut_stride_of(ix);
+    RET(sc.get(&dV, (size_t)nq * ix->p.d));
+    RET(sc.get(&dl, (size_t)nq * stride));
+    CK(cudaMemcpyAsync(dV, V, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
+    int launches = 0;
+    // computeLookupADC takes the ALREADY transformed vector (PQ.java:387): no permutation here
+    bool hp = ix->has_perm;
+    ix->has_perm = false;
+    int r = launch_lut(ix, dV, nullptr, nq, 1, dl, st, &launches);
+    ix->has_perm = hp;
+    RET(r);
+    CK(cudaMemcpy2DAsync(out, row * sizeof(double), dl, stride * sizeof(double), row * sizeof(double), (size_t)nq,
+                         cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ix->last_launches = launches;
+    return MMIDX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mmidx_size(mmidx_t *ix, int64_t *out) {
+    if (!ix || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    *out = ix->n;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_list_sizes(mmidx_t *ix, int32_t *out) {
+    if (!ix || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "only IVFPQ has inverted lists");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::fill(out, out + ix->p.nlist, 0);
+    for (int32_t l : ix->h_list) out[l]++;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_get_vector(mmidx_t *ix, int64_t iid, double *out) {
+    if (!ix || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_LINEAR) return fail(MMIDX_ERR_INVALID, "getVector applies to Linear only");
+    // Linear.java:254-256: "Internal id does not exist!"
+    if (iid < 0 || iid >= ix->n) return fail(MMIDX_ERR_INVALID, "Internal id does not exist!");
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    Scratch sc(st);
+    double *dv;
+    RET(sc.get(&dv, (size_t)ix->p.d));
+    k_linear_unpack_row<<<(ix->p.d + 255) / 256, 256, 0, st>>>(ix->dXb.as<double>(), ix->p.d, iid, dv);
+    RET(post_launch("k_linear_unpack_row", nullptr));
+    CK(cudaMemcpyAsync(out, dv, sizeof(double) * (size_t)ix->p.d, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_scan_bytes(mmidx_t *ix, int64_t nq, const double *Q, int64_t *out_total) {
+    if (!ix || !out_total) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type == MMIDX_LINEAR) {
+        *out_total = nq * ix->n_local * ix->p.d * 8;
+        return MMIDX_OK;
+    }
+    if (ix->p.type == MMIDX_PQ) {
+        *out_total = nq * ix->n_local * ix->code_bytes;
+        return MMIDX_OK;
+    }
+    int w = 0;
+    RET(validate_search(ix, nq, 1, &w));
+    std::vector<int32_t> probes((size_t)nq * w);
+    RET(mmidx_coarse_probe(ix, nq, Q, w, probes.data()));
+    std::vector<int32_t> len(ix->p.nlist);
+    RET(mmidx_list_sizes(ix, len.data()));
+    int64_t tot = 0;
+    for (size_t i = 0; i < probes.size(); ++i) tot += (int64_t)len[probes[i]] * (ix->code_bytes + 4);
+    *out_total = tot;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_last_timings(mmidx_t *ix, float *out5) {
+    if (!ix || !out5) return fail(MMIDX_ERR_INVALID, "null argument");
+    DeviceGuard g(ix->device);
+    for (int i = 0; i < 5; ++i) out5[i] = 0.f;
+    for (auto &s : ix->timer.spans) {
+        CK(cudaEventSynchronize(s.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s.a, s.b));
+        out5[s.stage] += ms;
+    }
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_last_launches(mmidx_t *ix, int32_t *out) {
+    if (!ix || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    *out = ix->last_launches;
+    return MMIDX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// VLAD (K7)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mmidx_vlad_dev(const double *d_codebook, int32_t K, int32_t D, int64_t n_img, const int64_t *d_offsets,
+                              int64_t n_desc, const double *d_desc, double *d_out, int32_t *d_assign, void *stream) {
+    if (K < 1 || D < 1 || n_img < 0 || n_desc < 0) return fail(MMIDX_ERR_INVALID, "bad VLAD geometry");
+    if (n_img == 0) return MMIDX_OK;
+    if (!d_codebook || !d_offsets || !d_out || (n_desc > 0 && !d_desc)) return fail(MMIDX_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc(st);
+    double *dBt;
+    int32_t *assign = d_assign, *order, *cstart;
+    RET(sc.get(&dBt, (size_t)K * D));
+    if (!assign) RET(sc.get(&assign, (size_t)n_desc));
+    RET(sc.get(&order, (size_t)n_desc));
+    RET(sc.get(&cstart, (size_t)n_img * (K + 1)));
+    k_transpose<<<(unsigned)(((size_t)K * D + 255) / 256), 256, 0, st>>>(d_codebook, K, D, dBt);
+    RET(post_launch("k_transpose", nullptr));
+    RET(launch_assign(d_desc, dBt, n_desc, K, D, assign, st, nullptr));
+    size_t smem = sizeof(int) * (size_t)(K + 1);
+    if (smem > 48 * 1024) RET(set_smem(k_vlad_order, smem));
+    for (int64_t i0 = 0; i0 < n_img; i0 += 1 << 30) {
+        int64_t nb = std::min<int64_t>(1 << 30, n_img - i0);
+        k_vlad_order<<<(unsigned)nb, MMIDX_NT, smem, st>>>(assign, d_offsets + i0, K, order, cstart + i0 * (K + 1));
+        RET(post_launch("k_vlad_order", nullptr));
+        k_vlad_accumulate<<<(unsigned)nb, MMIDX_NT, 0, st>>>(d_codebook, d_desc, d_offsets + i0, order, cstart + i0 * (K + 1), K, D,
+                                                            d_out + i0 * (int64_t)K * D);
+        RET(post_launch("k_vlad_accumulate", nullptr));
+    }
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_vlad(const double *codebook, int32_t K, int32_t D, int64_t n_img, const int64_t *offsets,
+                          const double *desc, double *out, int32_t *out_assign, int32_t device) {
+    if (K < 1 || D < 1 || n_img < 0) return fail(MMIDX_ERR_INVALID, "bad VLAD geometry");
+    if (n_img == 0) return MMIDX_OK;
+    if (!codebook || !offsets || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    RET(check_device(device));
+    DeviceGuard g(device);
+    for (int64_t i = 0; i < n_img; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(MMIDX_ERR_INVALID, "offsets must be non-decreasing");
+    if (offsets[0] != 0) return fail(MMIDX_ERR_INVALID, "offsets[0] must be 0");
+    const int64_t n_desc = offsets[n_img];
+    if (n_desc > 0 && !desc) return fail(MMIDX_ERR_INVALID, "null argument");
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = MMIDX_OK;
+    {
+        Scratch sc(st);
+        double *dcb, *ddesc, *dout;
+        int64_t *doff;
+        int32_t *dassign;
+        auto body = [&]() -> int {
+            RET(sc.get(&dcb, (size_t)K * D));
+            RET(sc.get(&ddesc, (size_t)std::max<int64_t>(n_desc, 1) * D));
+            RET(sc.get(&dout, (size_t)n_img * K * D));
+            RET(sc.get(&doff, (size_t)n_img + 1));
+            RET(sc.get(&dassign, (size_t)std::max<int64_t>(n_desc, 1)));
+            CK(cudaMemcpyAsync(dcb, codebook, sizeof(double) * (size_t)K * D, cudaMemcpyHostToDevice, st));
+            if (n_desc) CK(cudaMemcpyAsync(ddesc, desc, sizeof(double) * (size_t)n_desc * D, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(doff, offsets, sizeof(int64_t) * (size_t)(n_img + 1), cudaMemcpyHostToDevice, st));
+            RET(mmidx_vlad_dev(dcb, K, D, n_img, doff, n_desc, ddesc, dout, dassign, st));
+            CK(cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)n_img * K * D, cudaMemcpyDeviceToHost, st));
+            if (out_assign && n_desc)
+                CK(cudaMemcpyAsync(out_assign, dassign, sizeof(int32_t) * (size_t)n_desc, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            return MMIDX_OK;
+        };
+        rc = body();
+    }
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}

@@ -1,0 +1,221 @@
+// topk.cuh -- CTA-wide bounded top-k collector with the reference's BoundedPriorityQueue semantics.
+//
+// Replaces com.aliasi.util.BoundedPriorityQueue<Result> (LingPipe 4.0.1) as used at IVFPQ.java:409,445,
+// PQ.java:291,318, Linear.java:140,156 and IVFPQ.java:576,590.  Semantics restated in SURVEY.md A.2:
+//   * result = the k smallest distances; output order = ascending distance, later-offered first among ties;
+//   * only exact binary64 ties AT the k-th boundary depend on offer order.  The collector detects that case
+//     (flag "ambiguous") and the caller re-runs the query through the ordered tie pass (tie_resolve.cuh).
+//
+// Design: candidates that pass a running admission threshold are appended (warp-aggregated shared-memory
+// atomic) to an unordered buffer of CAP entries; when the buffer could overflow, an 8x8-bit radix select
+// finds the k-th smallest key and compacts in place.  Keys are the raw bits of non-negative doubles, whose
+// unsigned order equals the numeric order.  Every candidate carries its offer sequence number.
+#pragma once
+#include "common.cuh"
+
+namespace mmidx {
+
+template <int CAP>
+struct TopK {
+    static constexpr int ROUND = CAP / 2;     // max pushes between two maybe_compact() calls
+    static constexpr int KEEP_MAX = CAP / 2;  // entries kept by a compaction; k <= KEEP_MAX
+    static constexpr int PER = CAP / MMIDX_NT;
+
+    double dist[CAP];
+    unsigned long long seq[CAP];
+    int pay[CAP];
+    unsigned int hist[256];
+    double thr;       // admission threshold: an upper bound of the final k-th smallest distance
+    double tie_drop;  // distance at which entries tied with the threshold were discarded (-1: never)
+    int cnt;
+    int strict;  // 1: candidates equal to thr are no longer admitted (that tie is already flagged)
+    int s_bin, s_krem, s_bincnt, s_newcnt, s_tiecnt;
+
+    __device__ __forceinline__ void init() {
+        if (threadIdx.x == 0) {
+            thr = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+            tie_drop = -1.0;
+            cnt = 0;
+            strict = 0;
+        }
+    }
+
+    // to be called by all 32 lanes of a converged warp
+    __device__ __forceinline__ void push(bool pred, double d, unsigned long long s, int p) {
+        const unsigned full = 0xffffffffu;
+        unsigned mask = __ballot_sync(full, pred);
+        if (mask == 0) return;
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cnt, __popc(mask));
+        base = __shfl_sync(full, base, leader);
+        if (pred) {
+            int slot = base + __popc(mask & ((1u << lane) - 1u));
+            dist[slot] = d;
+            seq[slot] = s;
+            pay[slot] = p;
+        }
+    }
+
+    // k-th smallest key (1-based k) among the first n entries; all threads; n >= k >= 1
+    __device__ void select_kth(int n, int k, unsigned long long &kth, int &need, int &neq) {
+        const int tid = threadIdx.x;
+        unsigned long long prefix = 0;
+        unsigned krem = (unsigned)k;
+#pragma unroll 1
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += MMIDX_NT) {
+                unsigned long long key = (unsigned long long)__double_as_longlong(dist[i]);
+                if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                unsigned loc[8];
+                unsigned s = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    loc[b] = hist[tid * 8 + b];
+                    s += loc[b];
+                }
+                unsigned incl = s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                unsigned excl = incl - s;
+                if (excl < krem && krem <= incl) {
+                    unsigned r = krem - excl;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        if (r != 0u) {
+                            if (r <= loc[b]) {
+                                s_bin = tid * 8 + b;
+                                s_krem = (int)r;
+                                s_bincnt = (int)loc[b];
+                                r = 0u;
+                            } else {
+                                r -= loc[b];
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | (unsigned long long)s_bin;
+            krem = (unsigned)s_krem;
+        }
+        kth = prefix;
+        need = (int)krem;
+        neq = s_bincnt;
+        __syncthreads();  // s_* are rewritten by the next call
+    }
+
+    // keep every entry below the k-th smallest key plus at most (keep_max - #below) entries equal to it
+    __device__ void compact(int k, int keep_max) {
+        const int tid = threadIdx.x;
+        const int n = cnt;
+        unsigned long long kth;
+        int need, neq;
+        select_kth(n, k, kth, need, neq);
+        const int nless = k - need;
+        const int tie_room = keep_max - nless;
+        double d[PER];
+        unsigned long long s[PER];
+        int p[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            int i = tid + e * MMIDX_NT;
+            if (i < n) {
+                d[e] = dist[i];
+                s[e] = seq[i];
+                p[e] = pay[i];
+            }
+        }
+        if (tid == 0) {
+            s_newcnt = 0;
+            s_tiecnt = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            int i = tid + e * MMIDX_NT;
+            if (i < n) {
+                unsigned long long key = (unsigned long long)__double_as_longlong(d[e]);
+                bool keep = key < kth;
+                if (key == kth) keep = atomicAdd(&s_tiecnt, 1) < tie_room;
+                if (keep) {
+                    int slot = atomicAdd(&s_newcnt, 1);
+                    dist[slot] = d[e];
+                    seq[slot] = s[e];
+                    pay[slot] = p[e];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            cnt = s_newcnt;
+            thr = __longlong_as_double((long long)kth);
+            if (neq > tie_room) {
+                strict = 1;
+                tie_drop = thr;
+            } else {
+                strict = 0;
+            }
+        }
+        __syncthreads();
+    }
+
+    // block-uniform: compacts when fewer than ROUND free slots remain.  Contains the round barrier.
+    __device__ __forceinline__ void maybe_compact(int k) {
+        if (__syncthreads_or(*(volatile int *)&cnt > CAP - ROUND)) compact(k, KEEP_MAX);
+    }
+
+    // reduce to the final <=k entries, sorted in BoundedPriorityQueue iteration order
+    // (ascending distance; among equal distances the later-offered, i.e. larger seq, first).
+    // Returns the number of results; *ambiguous is set when an exact tie at the k-th boundary was cut.
+    __device__ int finalize(int k, bool *ambiguous) {
+        const int tid = threadIdx.x;
+        __syncthreads();
+        if (cnt > k) compact(k, k);
+        const int n = cnt;
+        int n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (int i = n + tid; i < n2; i += MMIDX_NT) {
+            dist[i] = __longlong_as_double(0x7ff0000000000000LL);
+            seq[i] = 0ull;
+            pay[i] = -1;
+        }
+        for (int size = 2; size <= n2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int t = tid; t < (n2 >> 1); t += MMIDX_NT) {
+                    int lo = 2 * t - (t & (stride - 1));
+                    int hi = lo + stride;
+                    bool up = (lo & size) == 0;
+                    double dl = dist[lo], dh = dist[hi];
+                    unsigned long long sl = seq[lo], sh = seq[hi];
+                    bool lo_after_hi = (dl > dh) || (dl == dh && sl < sh);
+                    if (lo_after_hi == up) {
+                        int pl = pay[lo], ph = pay[hi];
+                        dist[lo] = dh;
+                        dist[hi] = dl;
+                        seq[lo] = sh;
+                        seq[hi] = sl;
+                        pay[lo] = ph;
+                        pay[hi] = pl;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        *ambiguous = (n == k) && (tie_drop == dist[n - 1]);
+        return n;
+    }
+};
+
+}  // namespace mmidx

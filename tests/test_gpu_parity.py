@@ -1,0 +1,288 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs and against the committed golden vectors.  Bar (BASELINE.json north_star):
+bit-exact PQ codes / list ids and neighbour id sets, distances within 1e-4 relative.  This implementation is
+held to the stricter bar of bit-identical distances and identical result ORDER, because it reproduces the
+reference's binary64 operation order."""
+import os
+
+import numpy as np
+import pytest
+
+import mmidx_b200 as M
+import pyoracle as O
+from multimedia_indexing_b200 import _capi, synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-4  # north_star tolerance for distances (we assert equality first; this is the stated bound)
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"))
+
+
+def assert_same(res, ref, what=""):
+    iids, dist, cnt = res[:3]
+    oi, od, oc = ref
+    assert (cnt == oc).all(), f"{what}: result counts differ"
+    fin = np.isfinite(od)
+    assert np.allclose(dist[fin], od[fin], rtol=REL_TOL, atol=0), f"{what}: distances beyond 1e-4 relative"
+    for r in range(len(oc)):
+        assert set(iids[r, :oc[r]]) == set(oi[r, :oc[r]]), f"{what}: id set differs for query {r}"
+    assert (dist == od).all(), f"{what}: distances not bit-identical"
+    assert (iids == oi).all(), f"{what}: result order differs"
+
+
+def make_ivfpq(d, m, ks, nlist, w, Cq, P, perm=None, n=10 ** 6):
+    ix = M.IVFPQ(d, n, m, ks, M.TransformationType.None_, nlist)
+    ix.loadCoarseQuantizer(Cq)
+    ix.loadProductQuantizer(P)
+    if perm is not None:
+        ix.setPermutation(perm)
+    ix.setW(w)
+    return ix
+
+
+# ---------------------------------------------------------------- golden fixtures
+def test_linear_golden():
+    g = load("linear")
+    ix = M.Linear(g["X"].shape[1], 1000)
+    ix.indexVectors(None, g["X"])
+    k = int(g["k"])
+    assert_same(ix.searchBatch(k, g["Q"]), (g["ids"], g["dist"], np.full(len(g["Q"]), k, np.int32)), "linear golden")
+    assert (ix.getVector(17) == g["X"][17]).all()
+    a = ix.computeNearestNeighbors(k, "3")  # query by id -> getVector + search (Linear.java:181-184)
+    b = ix.computeNearestNeighbors(k, g["X"][3])
+    assert a.getIds() == b.getIds() and (a.getDistances() == b.getDistances()).all()
+
+
+@pytest.mark.parametrize("name", ["ivfpq_a", "ivfpq_perm"])
+def test_ivfpq_and_pq_golden(name):
+    g = load(name)
+    perm = g["perm"] if g["perm"].size else None
+    Cq, P, X, Q, k, w = g["Cq"], g["P"], g["X"], g["Q"], int(g["k"]), int(g["w"])
+    m, ks, S = P.shape
+    ix = make_ivfpq(X.shape[1], m, ks, Cq.shape[0], w, Cq, P, perm)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    assert (lists == g["lists"]).all() and (codes == g["codes"]).all()
+    assert (ix.computeNearestCoarseIndices(Q) == g["probes"]).all()
+    assert_same(ix.searchBatch(k, Q), (g["ids"], g["dist"], g["cnt"]), name)
+    assert (ix.computeLookupADC(Q[:1])[0] == g["lut0"]).all()
+    pq = M.PQ(X.shape[1], 1000, m, ks)
+    pq.loadProductQuantizer(P)
+    if perm is not None:
+        pq.setPermutation(perm)
+    _, pc = pq.indexVectors(None, X, return_codes=True)
+    assert (pc == g["pq_codes"]).all()
+    assert_same(pq.searchBatch(k, Q), (g["pq_ids"], g["pq_dist"], np.full(len(Q), k, np.int32)), name + " flat PQ")
+
+
+def test_vlad_golden():
+    g = load("vlad")
+    agg = M.VladAggregator(g["codebook"])
+    out, assign = agg.aggregateBatch((g["desc"], g["offsets"]), return_assign=True)
+    assert (out == g["out"]).all()
+    assert (agg.aggregate(np.zeros((0, 6))) == 0).all()
+    _, oa = O.vlad(g["codebook"], g["desc"], g["offsets"])
+    assert (assign == oa).all()
+
+
+# ---------------------------------------------------------------- seeded comparisons against the oracle
+CASES = [
+    # d, m, ks, nlist, w, n, nq, k, perm
+    (32, 4, 64, 32, 8, 6000, 40, 10, False),
+    (128, 8, 256, 64, 16, 20000, 64, 100, False),   # north-star geometry, scaled down
+    (128, 16, 256, 32, 8, 8000, 32, 100, True),     # config-4 geometry (m=16) + RandomPermutation
+    (24, 3, 300, 8, 8, 3000, 16, 20, False),        # ks > 256 -> short codes, w == nlist
+    (20, 5, 7, 5, 2, 500, 9, 600, False),           # k > candidates, odd m*ks, k > 512
+    (64, 8, 256, 16, 4, 5000, 3, 1, False),         # k = 1
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_ivfpq_vs_oracle(case):
+    d, m, ks, nlist, w, n, nq, k, use_perm = case
+    ce = synth.mixture_centers(d, 64)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=min(n, 5000), iters=4, centers=ce)
+    perm = M.random_permutation(1, d) if use_perm else None
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P, perm)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    ol, oc = O.ivfpq_encode(Cq, P, X, perm, threads=8)
+    assert (lists == ol).all(), "coarse list ids differ"
+    assert (codes == oc).all(), "PQ codes differ"
+    assert (ix.listSizes() == np.bincount(ol, minlength=nlist)).all()
+    assert (ix.computeNearestCoarseIndices(Q) == O.coarse_topw(Cq, Q, w)).all()
+    off, cc, ii = synth.csr_from_assignments(ol, oc, nlist)
+    assert_same(ix.searchBatch(k, Q), O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, perm, threads=8), "ivfpq")
+    # encode-only entry point gives the same codes without storing
+    l2, c2 = ix.encode(X[:100])
+    assert (l2 == ol[:100]).all() and (c2 == oc[:100]).all() and ix.getLoadCounter() == n
+
+
+@pytest.mark.parametrize("d,m,ks,n,nq,k", [(32, 4, 64, 7000, 20, 10), (128, 8, 256, 30000, 16, 100), (16, 2, 1000, 2000, 8, 5)])
+def test_pq_vs_oracle(d, m, ks, n, nq, k):
+    ce = synth.mixture_centers(d, 64)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
+    P = synth.train_pq(d, m, ks, ntrain=min(n, 5000), iters=4, centers=ce)
+    pq = M.PQ(d, n, m, ks)
+    pq.loadProductQuantizer(P)
+    _, codes = pq.indexVectors(None, X, return_codes=True)
+    oc = O.pq_encode(P, X, threads=8)
+    assert (codes == oc).all()
+    assert_same(pq.searchBatch(k, Q), O.pq_search(P, oc, Q, k, threads=8), "pq")
+    luts = pq.computeLookupADC(Q[:3])
+    for i in range(3):
+        assert (luts[i] == O.pq_lut(P, Q[i])).all()
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(10000, 64, 50, 10), (777, 5, 7, 1000), (4097, 128, 3, 100)])
+def test_linear_vs_oracle(n, d, nq, k):
+    ce = synth.mixture_centers(d, 64)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
+    ix = M.Linear(d, n)
+    ix.indexVectors(None, X[: n // 2])
+    ix.indexVectors(None, X[n // 2:])  # two appends: exercises the packed-block growth
+    assert_same(ix.searchBatch(k, Q), O.linear_search(X, Q, k, threads=8), "linear")
+
+
+def test_ties_at_the_kth_boundary_follow_the_queue_rules():
+    """Exact duplicates -> many exact binary64 ties, including at the k-th boundary."""
+    rng = np.random.default_rng(3)
+    d, m, ks, nlist, w, k = 16, 4, 16, 6, 6, 25
+    base = np.clip(np.rint(rng.normal(64, 20, size=(40, d))), 0, 255)
+    X = base[rng.integers(0, 40, size=3000)]  # every vector repeated ~75 times
+    Q = base[:10] + 1.0
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=2000, iters=3, centers=base)
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    assert_same(ix.searchBatch(k, Q), O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w), "ivfpq ties")
+    pq = M.PQ(d, 5000, m, ks)
+    pq.loadProductQuantizer(P)
+    _, pc = pq.indexVectors(None, X, return_codes=True)
+    assert_same(pq.searchBatch(k, Q), O.pq_search(P, pc, Q, k), "pq ties")
+    lin = M.Linear(d, 5000)
+    lin.indexVectors(None, X)
+    assert_same(lin.searchBatch(k, Q), O.linear_search(X, Q, k), "linear ties")
+    # coarse ties: duplicated coarse centroids
+    Cd = np.vstack([Cq[:3], Cq[:3]])
+    ix2 = make_ivfpq(d, m, ks, 6, 3, Cd, P)
+    assert (ix2.computeNearestCoarseIndices(Q) == O.coarse_topw(Cd, Q, 3)).all()
+
+
+def test_bulk_reload_matches_incremental_index():
+    """indexPQCode / loadIndexInMemory path (IVFPQ.java:357-386, 680-728)."""
+    d, m, ks, nlist, w, k = 32, 4, 64, 16, 4, 10
+    ce = synth.mixture_centers(d, 32)
+    X, Q = synth.mixture(3000, d, 1, ce), synth.mixture(12, d, 2, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=3000, iters=3, centers=ce)
+    a = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = a.indexVectors(None, X, return_codes=True)
+    b = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    b.indexPQCodes(None, lists[:1000], codes[:1000])
+    for i in range(1000, 1010):  # the reference's single-item form with Java signed bytes
+        assert b.indexPQCode(str(i), int(lists[i]), (codes[i].astype(np.int16) - 128).astype(np.int8))
+    assert not b.indexPQCode("1005", 0, np.zeros(m, np.int8))  # duplicate id -> False (ASS.java:237-240)
+    b.indexPQCodes(None, lists[1010:], codes[1010:])
+    ra, rb = a.searchBatch(k, Q), b.searchBatch(k, Q)
+    assert (ra[0] == rb[0]).all() and (ra[1] == rb[1]).all()
+    # search, add more, search again: re-seal keeps insertion order
+    a.indexVectors(None, X[:500] + 1.0)
+    X2 = np.vstack([X, X[:500] + 1.0])
+    ol, oc = O.ivfpq_encode(Cq, P, X2, threads=8)
+    off, cc, ii = synth.csr_from_assignments(ol, oc, nlist)
+    assert_same(a.searchBatch(k, Q), O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w), "after second add")
+
+
+def test_reference_api_surface_and_errors():
+    d, m, ks, nlist = 16, 4, 16, 20
+    ce = synth.mixture_centers(d, 16)
+    X = synth.mixture(50, d, 1, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=500, iters=2, centers=ce)
+    ix = M.IVFPQ(d, 30, m, ks, M.TransformationType.None_, nlist)
+    with pytest.raises(M.MmidxError) as e:  # quantizers not loaded
+        ix.indexVector("a", X[0])
+    assert e.value.code == _capi.ERR_STATE
+    ix.loadCoarseQuantizer(Cq)
+    ix.loadProductQuantizer(P)
+    assert ix.w == 2  # default w = (int)(nlist * 0.1), IVFPQ.java:188
+    assert ix.indexVector("img0", X[0]) is True
+    assert ix.indexVector("img0", X[1]) is False  # duplicate id
+    with pytest.raises(M.MmidxError) as e:
+        ix.indexVector("bad", X[0][:5])
+    assert "dimensionality of the vector is wrong" in str(e.value)
+    for i in range(1, 30):
+        assert ix.indexVector(f"img{i}", X[i])
+    assert ix.indexVector("img30", X[30]) is False  # full (ASS.java:232-235)
+    assert ix.getLoadCounter() == 30 and ix.getInternalId("img7") == 7 and ix.getId(7) == "img7"
+    ans = ix.computeNearestNeighbors(5, X[3])
+    assert len(ans.getIds()) <= 5 and all(s.startswith("img") for s in ans.getIds())
+    assert (np.diff(ans.getDistances()) >= 0).all()
+    ix.setW(0)
+    with pytest.raises(M.MmidxError) as e:  # BoundedPriorityQueue ctor throws for size 0
+        ix.computeNearestNeighbors(5, X[3])
+    assert e.value.code == _capi.ERR_W
+    ix.setW(nlist + 1)
+    with pytest.raises(M.MmidxError) as e:  # NPE in the reference (IVFPQ.java:598)
+        ix.computeNearestNeighbors(5, X[3])
+    assert e.value.code == _capi.ERR_W
+    ix.setW(nlist)
+    with pytest.raises(M.MmidxError):
+        ix.computeNearestNeighbors(0, X[3])
+    # w = nlist with 30 vectors: fewer candidates than k
+    ans = ix.computeNearestNeighbors(100, X[3])
+    assert len(ans.getIds()) == 30
+    ix.close()
+    # empty index
+    e2 = M.PQ(d, 10, m, ks)
+    e2.loadProductQuantizer(P)
+    iids, dist, cnt, _ = e2.searchBatch(3, X[:2])
+    assert (cnt == 0).all() and (iids == -1).all() and np.isinf(dist).all()
+
+
+def test_vlad_vs_oracle_ragged():
+    K, D = 128, 64
+    desc, offsets = synth.descriptors(40, D, mean=300, sd=150)
+    offsets = np.concatenate([offsets[:10], [offsets[9]], offsets[10:]])  # insert an empty image
+    cb = synth.kmeans(desc[:5000], K, 5, seed=1)
+    agg = M.VladAggregator(cb)
+    out, assign = agg.aggregateBatch((desc, offsets), return_assign=True)
+    oo, oa = O.vlad(cb, desc, offsets, threads=8)
+    assert (assign == oa).all(), "centroid assignment differs"
+    assert (out == oo).all(), "VLAD vectors not bit-identical"
+    assert (out[9] == 0).all()
+    one = agg.aggregate(desc[offsets[3]:offsets[4]])
+    assert (one == oo[3]).all()
+    with pytest.raises(M.MmidxError):
+        agg.aggregate(np.zeros((3, D + 1)))
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE configs)
+def test_full_size_config3_properties():
+    """IVFPQ 1M x 128, nlist=1024, w=32, m=8, top-100: oracle agreement on a query sample + size-independent
+    properties (sortedness, ids inside probed lists, idempotence, sharding-by-probe additivity)."""
+    d, m, ks, nlist, w, k, n, nq = 128, 8, 256, 1024, 32, 100, 1_000_000, 2000
+    ce = synth.mixture_centers(d)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=50_000, iters=8, centers=ce)
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P, n=n)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    assert ix.getLoadCounter() == n and (ix.listSizes() == np.bincount(lists, minlength=nlist)).all()
+    sel = np.random.default_rng(0).choice(n, 3000, replace=False)
+    ol, oc = O.ivfpq_encode(Cq, P, X[sel], threads=O.num_threads())
+    assert (lists[sel] == ol).all() and (codes[sel] == oc).all()
+    iids, dist, cnt, _ = ix.searchBatch(k, Q)
+    assert (cnt == k).all() and (np.diff(dist, axis=1) >= 0).all()
+    probes = ix.computeNearestCoarseIndices(Q)
+    for r in range(0, nq, 97):
+        assert np.isin(lists[iids[r]], probes[r]).all()
+        assert len(set(iids[r])) == k
+    again = ix.searchBatch(k, Q)
+    assert (again[0] == iids).all() and (again[1] == dist).all()
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    ref = O.ivfpq_search(Cq, P, off, cc, ii, Q[:200], k, w, threads=O.num_threads())
+    assert_same((iids[:200], dist[:200], cnt[:200]), ref, "config 3 sample")
+    # single query == row of the batch
+    one = ix.searchBatch(k, Q[5:6])
+    assert (one[0][0] == iids[5]).all() and (one[1][0] == dist[5]).all()
