@@ -38,6 +38,8 @@ struct TopK {
             cnt = 0;
             strict = 0;
         }
+        // other threads must not evaluate maybe_compact()'s predicate on uninitialised shared memory
+        __syncthreads();
     }
 
     // to be called by all 32 lanes of a converged warp

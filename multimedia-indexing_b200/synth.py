@@ -6,6 +6,7 @@ k-means (numpy) from a seeded sample; the reference learns them offline with Wek
 scope) -- parity only needs both sides to consume the SAME codebooks.  Residuals use the reference's sign,
 centroid - vector (IVFPQ.java:642-648, ResidualVectorComputation.java:34)."""
 import numpy as np
+from scipy import sparse
 
 SEED_DB, SEED_Q, SEED_TRAIN, SEED_DESC, SEED_CENTERS = 1, 2, 3, 4, 5
 
@@ -28,9 +29,12 @@ def mixture(n, d, seed, centers=None, chunk=1 << 17):
 
 def _assign(X, C):
     # argmin ||x - c||^2 via the expansion (training only; ties/rounding irrelevant here)
-    x2 = (X * X).sum(1)[:, None]
     c2 = (C * C).sum(1)[None, :]
-    return np.argmin(x2 - 2.0 * (X @ C.T) + c2, axis=1)
+    Ct2 = np.ascontiguousarray(-2.0 * C.T)
+    out = np.empty(X.shape[0], dtype=np.int64)
+    for b in range(0, X.shape[0], 4096):  # row blocks keep the [block][k] temporary cache-resident
+        out[b:b + 4096] = np.argmin(X[b:b + 4096] @ Ct2 + c2, axis=1)
+    return out
 
 
 def kmeans(X, k, iters=20, seed=0):
@@ -41,8 +45,8 @@ def kmeans(X, k, iters=20, seed=0):
     for _ in range(iters):
         a = _assign(X, C)
         cnt = np.bincount(a, minlength=k)
-        S = np.zeros_like(C)
-        np.add.at(S, a, X)
+        onehot = sparse.csr_matrix((np.ones(X.shape[0]), (a, np.arange(X.shape[0]))), shape=(k, X.shape[0]))
+        S = onehot @ X
         nz = cnt > 0
         C[nz] = S[nz] / cnt[nz, None]
         if (~nz).any():  # re-seed empty clusters

@@ -286,3 +286,20 @@ def test_full_size_config3_properties():
     # single query == row of the batch
     one = ix.searchBatch(k, Q[5:6])
     assert (one[0][0] == iids[5]).all() and (one[1][0] == dist[5]).all()
+
+
+def test_large_batch_single_split_path():
+    """>= 592 queries in one chunk -> one CTA per query (nsplit == 1) and large select/merge grids.  Regression:
+    TopK::init() lacked a barrier, so a CTA could act on a previous CTA's shared-memory garbage."""
+    d, m, ks, nlist, w, n, nq, k = 64, 8, 256, 256, 16, 60000, 3000, 100
+    ce = synth.mixture_centers(d, 512)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=10000, iters=4, centers=ce)
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    for _ in range(3):
+        assert (ix.computeNearestCoarseIndices(Q) == O.coarse_topw(Cq, Q, w)).all()
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    ref = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=O.num_threads())
+    for _ in range(2):
+        assert_same(ix.searchBatch(k, Q), ref, "nsplit=1")

@@ -1,0 +1,83 @@
+"""Multi-GPU parity (needs >= 2 B200: gpurun --gpus 2): IVF lists sharded over 2 ranks, NCCL all-gather of the
+per-shard top-k, device merge, and the sharded tie pass -- against the unsharded CPU oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        import sys
+        import torch.distributed as dist
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        for p in (root, os.path.join(root, "oracle")):
+            sys.path.insert(0, p)
+        import mmidx_b200 as M
+        import pyoracle as O
+        from multimedia_indexing_b200 import synth
+        from multimedia_indexing_b200.sharded import ShardedIVFPQ
+
+        ok = True
+        msgs = []
+        for case in ("plain", "ties"):
+            d, m, ks, nlist, w, k, n, nq = 64, 8, 256, 64, 16, 100, 30000, 700
+            ce = synth.mixture_centers(d, 128)
+            if case == "plain":
+                X, Q = synth.mixture(n, d, 1, ce), synth.mixture(nq, d, 2, ce)
+            else:  # heavy duplication -> exact ties at the k-th boundary across shards
+                base = synth.mixture(60, d, 1, ce)
+                X = base[np.random.default_rng(1).integers(0, 60, size=n)]
+                Q = base[:40] + 1.0
+                nq, k = 40, 25
+            Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=5000, iters=3, centers=ce)
+            sh = ShardedIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist)
+            sh.loadCoarseQuantizer(Cq)
+            sh.loadProductQuantizer(P)
+            sh.setW(w)
+            lists, codes = sh.indexVectors(None, X, return_codes=True)
+            dQ = torch.from_numpy(Q).cuda()
+            iids, dd, cnt = sh.search(k, dQ)
+            off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+            oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=8)
+            same = (iids.cpu().numpy() == oi).all() and (dd.cpu().numpy() == od).all() and (cnt.cpu().numpy() == oc).all()
+            ok &= bool(same)
+            msgs.append(f"{case}: equal={bool(same)} local_vectors={int(sh.listSizes().sum())}")
+            ok &= int(sh.listSizes().sum()) < n  # really sharded
+            sh.close()
+        q.put((rank, ok, msgs))
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, False, f"{e}\n{traceback.format_exc()}"))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_ivfpq_two_gpus():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] is True for r in res), res
