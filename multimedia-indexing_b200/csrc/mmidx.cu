@@ -151,7 +151,7 @@ struct mmidx_index {
     std::mutex mu;
     StageTimer timer;
     int last_launches = 0;
-    size_t lut_chunk_bytes = (size_t)64 << 20;
+    size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
 };
 
 struct Launches {
