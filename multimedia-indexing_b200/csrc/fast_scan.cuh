@@ -1,0 +1,576 @@
+// fast_scan.cuh -- fused IVFADC search kernel: fp32 ADC filter + exact binary64 verification.
+//
+// Replaces k_lut_build + k_ivfpq_scan for the common geometry (ks <= 256, m in {8,16}) and returns the SAME
+// bits: a candidate is only ever accepted on its exact binary64 distance, computed in the reference's
+// operation order (computeResidualVector IVFPQ.java:642-648, computeLookupADC :525-538, ADC sum :435-438).
+// The fp32 table is used to REJECT candidates that provably cannot enter the queue.
+//
+// Per probe the reference builds LUT[j][c] = sum_t ((C_l - q)[jS+t] - P[j][c][t])^2 (m*ks*S triples).  Here
+//   LUT[j][c] = T1[l][j][c] + T2[q][j][c] + s[q][l][j]
+//     T1 = ||C_l,j - P_j,c||^2          per index  (k_build_t1, binary64 then rounded to fp32; nlist*m*ks floats)
+//     T2 = 2 q_j . P_j,c                per query  (fp32 FMA chain in the kernel prologue)
+//     s  = sum_t q_t (q_t - 2 C_l,t)    per probe  (binary64, m values)
+// so a probe costs one 4*m*ks-byte TMA load of T1[l] and two fp32 adds per entry.
+//
+// Error bound (u = 2^-24; derivation in DESIGN.md 5.1): every fp32 entry differs from the real LUT value by
+// at most u*1.002*(3*T1 + (2S+8)*||q_j||*||P_j,c|| + 2|s_j|), and an m-term fp32 sum adds m*u*d32.  With
+//   Bq  = 1.02 * u * sum_j max_probes (3*T1max[l][j] + (4S+14)*||q_j||*Pmax[j] + 2|s_j|),   rel = m*u
+// the exact distance of a candidate lies in [d32 - rel*d32 - Bq, d32 + rel*d32 + Bq].  Both ends are monotone
+// in d32, so the whole selection runs on fp32 keys: if x is the k-th smallest d32 seen so far, U = x*(1+rel)+Bq
+// bounds the final k-th exact distance from above and every candidate with d32 > (U+Bq)*(1+2rel) is provably
+// outside the result.  The collector keeps everything at or below that slack line (k entries plus the few inside
+// the error band); only those survivors (~k per query) are evaluated exactly at the end.  If the band ever holds
+// more entries than the collector can keep (massive exact duplicates) the query is handed to the direct kernel.
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tie_resolve.cuh"
+#include "topk.cuh"
+
+namespace mmidx {
+
+// ---- index-time tables ------------------------------------------------------------------------------
+// T1[l][j*ks + c] and t1max[l][j] (must be zero-filled before launch).  grid (nlist, m), thread <-> c.
+__global__ void __launch_bounds__(MMIDX_NT) k_build_t1(const double *__restrict__ C, const double *__restrict__ P,
+                                                       const int32_t *__restrict__ perm, int d, int m, int ks, int S,
+                                                       float *__restrict__ T1, float *__restrict__ t1max) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *cv = reinterpret_cast<double *>(smem_raw);  // [S] sub-vector of the (permuted) coarse centroid
+    const int l = blockIdx.x, j = blockIdx.y;
+    for (int t = threadIdx.x; t < S; t += MMIDX_NT) {
+        int src = j * S + t;
+        if (perm) src = perm[src];
+        cv[t] = C[(int64_t)l * d + src];
+    }
+    __syncthreads();
+    float mx = 0.f;
+    for (int c = threadIdx.x; c < ks; c += MMIDX_NT) {
+        const double *pc = P + ((int64_t)j * ks + c) * S;
+        double acc = 0.0;
+        for (int t = 0; t < S; ++t) acc = sqacc(acc, cv[t], pc[t]);
+        float f = __double2float_rn(acc);
+        T1[(int64_t)l * m * ks + (int64_t)j * ks + c] = f;
+        mx = fmaxf(mx, f);
+    }
+    // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<int *>(&t1max[(int64_t)l * m + j]), __float_as_int(mx));
+}
+
+// P32t[j][t][c] = fp32(P[j][c][t]) (thread <-> c reads coalesce) and pmax[j] >= max_c ||P_j,c||. grid m.
+__global__ void __launch_bounds__(MMIDX_NT) k_build_p32t(const double *__restrict__ P, int m, int ks, int S,
+                                                         float *__restrict__ P32t, float *__restrict__ pmax) {
+    const int j = blockIdx.x;
+    float mx = 0.f;
+    for (int c = threadIdx.x; c < ks; c += MMIDX_NT) {
+        const double *pc = P + ((int64_t)j * ks + c) * S;
+        double n2 = 0.0;
+        for (int t = 0; t < S; ++t) {
+            P32t[((int64_t)j * S + t) * ks + c] = __double2float_rn(pc[t]);
+            n2 += pc[t] * pc[t];
+        }
+        mx = fmaxf(mx, __double2float_ru(sqrt(n2) * (1.0 + 1e-12)));
+    }
+    atomicMax(reinterpret_cast<int *>(&pmax[j]), __float_as_int(mx));
+}
+
+struct FastArgs {
+    const double *Q;          // [nq][d]
+    const double *C;          // [nlist][d]
+    const double *P;          // [m][ks][S]
+    const float *T1;          // [nlist][m*ks]
+    const float *P32t;        // [m][S][ks]
+    const float *t1max;       // [nlist][m]
+    const float *pmax;        // [m]
+    const int32_t *perm;      // [d] or NULL
+    const int32_t *probes;    // [nq][w]
+    const uint8_t *codes;     // CSR
+    const int32_t *iids;
+    const int64_t *list_off;
+    const int32_t *list_len;
+    int d, m, ks, S, w, k, nsplit;
+    int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
+    int32_t *fb_count;
+    unsigned long long *stats;  // optional [4]: candidates, collector pushes, exact evaluations, overflows
+};
+
+// order-preserving map of fp32 bit patterns to unsigned keys (d32 may be slightly negative)
+__device__ __forceinline__ unsigned f32_key(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unkey(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// CTA-wide collector on fp32 keys with an error-band slack (see the header comment).
+template <int CAP>
+struct TopK32 {
+    static constexpr int ROUND = CAP / 2;
+    static constexpr int KEEP_MAX = CAP / 2;
+    static constexpr int PER = CAP / MMIDX_NT;
+    float key[CAP];
+    int pos[CAP];
+    int probe[CAP];
+    unsigned int hist[256];
+    float thr32;  // admission threshold: candidates with d32 > thr32 are provably outside the result
+    int cnt, overflow;
+    int s_bin, s_krem, s_newcnt;
+
+    __device__ __forceinline__ void init() {
+        if (threadIdx.x == 0) {
+            thr32 = __int_as_float(0x7f800000);
+            cnt = 0;
+            overflow = 0;
+        }
+        __syncthreads();
+    }
+
+    // all 32 lanes of a converged warp
+    __device__ __forceinline__ void push(bool pred, float d, int ps, int pb) {
+        const unsigned mask = __ballot_sync(0xffffffffu, pred);
+        if (mask == 0) return;
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cnt, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pred) {
+            const int slot = base + __popc(mask & ((1u << lane) - 1u));
+            key[slot] = d;
+            pos[slot] = ps;
+            probe[slot] = pb;
+        }
+    }
+
+    // k-th smallest key (1-based) among the first n entries, n >= k >= 1; 4 radix passes of 8 bits
+    __device__ float select_kth(int n, int k) {
+        const int tid = threadIdx.x;
+        unsigned prefix = 0, krem = (unsigned)k;
+#pragma unroll 1
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += MMIDX_NT) {
+                const unsigned kk = f32_key(key[i]);
+                if (pass == 0 || (kk >> (shift + 8)) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                unsigned loc[8], sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    loc[b] = hist[tid * 8 + b];
+                    sum += loc[b];
+                }
+                unsigned incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                const unsigned excl = incl - sum;
+                if (excl < krem && krem <= incl) {
+                    unsigned r = krem - excl;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        if (r != 0u) {
+                            if (r <= loc[b]) {
+                                s_bin = tid * 8 + b;
+                                s_krem = (int)r;
+                                r = 0u;
+                            } else {
+                                r -= loc[b];
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | (unsigned)s_bin;
+            krem = (unsigned)s_krem;
+        }
+        __syncthreads();
+        return f32_unkey(prefix);
+    }
+
+    // keep every entry at or below the slack line of the k-th smallest key
+    __device__ void compact(int k, double bq, double rel) {
+        const int tid = threadIdx.x;
+        const int n = cnt;
+        const float kth = select_kth(n, k);
+        const double U = (double)kth + rel * fabs((double)kth) + bq;
+        const float keep32 = __double2float_ru((U + bq) * (1.0 + 2.0 * rel));
+        float d[PER];
+        int ps[PER], pb[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = tid + e * MMIDX_NT;
+            if (i < n) {
+                d[e] = key[i];
+                ps[e] = pos[i];
+                pb[e] = probe[i];
+            }
+        }
+        if (tid == 0) s_newcnt = 0;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = tid + e * MMIDX_NT;
+            if (i < n && d[e] <= keep32) {
+                const int slot = atomicAdd(&s_newcnt, 1);
+                if (slot < KEEP_MAX) {
+                    key[slot] = d[e];
+                    pos[slot] = ps[e];
+                    probe[slot] = pb[e];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (s_newcnt > KEEP_MAX) overflow = 1;  // the error band holds more than we can keep: direct kernel
+            cnt = min(s_newcnt, KEEP_MAX);
+            thr32 = keep32;
+        }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void maybe_compact(int k, double bq, double rel) {
+        if (__syncthreads_or(*(volatile int *)&cnt > CAP - ROUND)) compact(k, bq, rel);
+    }
+};
+
+// exact binary64 ADC distance of one stored code, straight from the quantizers (reference operation order)
+__device__ __forceinline__ double exact_adc(const double *__restrict__ Cl, const double *__restrict__ qv,
+                                            const int32_t *__restrict__ perm, const double *__restrict__ P,
+                                            const uint8_t *__restrict__ code, int m, int ks, int S) {
+    double dist = 0.0;
+    for (int j = 0; j < m; ++j) {
+        const double *pc = P + ((int64_t)j * ks + code[j]) * S;
+        double acc = 0.0;
+        for (int t = 0; t < S; ++t) {
+            int src = j * S + t;
+            if (perm) src = perm[src];
+            // residual = centroid - query (one rounding), then (r - p)^2 accumulated in order
+            double r = __dsub_rn(Cl[src], qv[src]);
+            acc = sqacc(acc, r, pc[t]);
+        }
+        dist = __dadd_rn(dist, acc);
+    }
+    return dist;
+}
+
+// The same value computed by one warp with coalesced loads: lane <-> term (j, t); the squared terms are staged
+// in shared memory (xs[m][S+1]) and summed in index order by lane j, then lane 0 adds the m sub-sums in order.
+// Returns the distance in every lane.  xs is private to the warp.
+__device__ __forceinline__ double exact_adc_warp(const double *__restrict__ Cl, const double *__restrict__ qv,
+                                                 const int32_t *__restrict__ perm, const double *__restrict__ P,
+                                                 const uint8_t *__restrict__ code, int m, int ks, int S,
+                                                 double *xs) {
+    const int lane = threadIdx.x & 31;
+    const int d = m * S;
+    for (int e = lane; e < d; e += 32) {
+        const int j = e / S, t = e - j * S;
+        int src = e;
+        if (perm) src = perm[src];
+        const double r = __dsub_rn(Cl[src], qv[src]);
+        const double p = P[((int64_t)j * ks + code[j]) * S + t];
+        const double a = __dsub_rn(r, p);
+        xs[j * (S + 1) + t] = __dmul_rn(a, a);
+    }
+    __syncwarp();
+    double acc = 0.0;
+    if (lane < m)
+        for (int t = 0; t < S; ++t) acc = __dadd_rn(acc, xs[lane * (S + 1) + t]);
+    double dist = 0.0;
+    for (int j = 0; j < m; ++j) dist = __dadd_rn(dist, __shfl_sync(0xffffffffu, acc, j));
+    __syncwarp();
+    return dist;
+}
+
+template <int CAP32>
+struct FastExactCap {
+    static constexpr int value = (CAP32 / 2 <= 512) ? 512 : CAP32 / 2;  // exact collector holds the survivors
+};
+
+// grid (nsplit, nq).  CTA (s, q) handles probes s, s+nsplit, ... of query q in rank order.
+template <int CAP32, int M>
+__global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
+    constexpr int ECAP = FastExactCap<CAP32>::value;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TopK32<CAP32> &c32 = *reinterpret_cast<TopK32<CAP32> *>(smem_raw);
+    const size_t c32_bytes = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
+    const int nent = M * a.ks;
+    // region A (scan phase): t2 | lut0 | lut1.   Aliased in the final phase by: TopK<ECAP> | per-warp xs
+    unsigned char *regA = smem_raw + c32_bytes;
+    float *t2 = reinterpret_cast<float *>(regA);   // [nent]
+    float *lut0 = t2 + nent;                       // [nent]  (TMA target, then LUT in place)
+    float *lut1 = lut0 + nent;                     // [nent]
+    const size_t tk_bytes = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
+    const size_t xs_bytes = (size_t)(MMIDX_NT / 32) * M * (a.S + 1) * sizeof(double);
+    const size_t regA_bytes = max((size_t)3 * nent * sizeof(float), tk_bytes + xs_bytes);
+    double *qv = reinterpret_cast<double *>(regA + ((regA_bytes + 15) & ~(size_t)15));  // [d] raw query
+    double *qn = qv + a.d;                                                             // [M] ||q_j||
+    double *sj = qn + M;                                                               // [M] s of the current probe
+    float *bterm = reinterpret_cast<float *>(sj + M);                                  // [M] max_p error term
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bterm + M + (M & 1));                // [2]
+    double *s_bq = reinterpret_cast<double *>(bars + 2);
+
+    const int tid = threadIdx.x;
+    const int s = blockIdx.x;
+    const int64_t q = blockIdx.y;
+    const int32_t *pr = a.probes + q * a.w;
+    const uint32_t t1_bytes = (uint32_t)(nent * sizeof(float));
+    const int S = a.S, ks = a.ks;
+    const double rel = (double)M * 5.9604644775390625e-08;
+
+    c32.init();
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    if (tid < M) bterm[tid] = 0.f;
+    for (int i = tid; i < a.d; i += MMIDX_NT) qv[i] = a.Q[q * (int64_t)a.d + i];
+    __syncthreads();
+    if (tid == 0 && s < a.w) {
+        mbar_arrive_expect_tx(&bars[0], t1_bytes);
+        tma_load_1d(lut0, a.T1 + (int64_t)pr[s] * nent, t1_bytes, &bars[0]);
+    }
+    // ---- per-query prologue: T2[j][c] = 2 * sum_t q32[perm(jS+t)] * P32t[j][t][c];  ||q_j||;  error radius Bq ----
+    for (int e = tid; e < nent; e += MMIDX_NT) {
+        const int j = e / ks, c = e - j * ks;
+        const float *pp = a.P32t + (int64_t)j * S * ks + c;
+        float acc = 0.f;
+        for (int t = 0; t < S; ++t) {
+            int src = j * S + t;
+            if (a.perm) src = a.perm[src];
+            acc = fmaf(__double2float_rn(qv[src]), pp[(int64_t)t * ks], acc);
+        }
+        t2[e] = 2.f * acc;
+    }
+    if (tid < M) {
+        double n2 = 0.0;
+        for (int t = 0; t < S; ++t) {
+            int src = tid * S + t;
+            if (a.perm) src = a.perm[src];
+            n2 += qv[src] * qv[src];
+        }
+        qn[tid] = sqrt(n2) * (1.0 + 1e-12);
+    }
+    __syncthreads();
+    for (int e = tid; e < a.w * M; e += MMIDX_NT) {  // (probe, j) pairs of this query (all splits: same Bq)
+        const int p = e / M, j = e - p * M;
+        const int l = pr[p];
+        const double *Cl = a.C + (int64_t)l * a.d;
+        double acc = 0.0;
+        for (int t = 0; t < S; ++t) {
+            int src = j * S + t;
+            if (a.perm) src = a.perm[src];
+            const double qt = qv[src];
+            acc += qt * (qt - 2.0 * Cl[src]);
+        }
+        const double term = 3.0 * (double)a.t1max[(int64_t)l * M + j] + (4.0 * S + 14.0) * qn[j] * (double)a.pmax[j] +
+                            2.0 * fabs(acc);
+        atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double b = 0.0;
+        for (int j = 0; j < M; ++j) b += (double)bterm[j];
+        *s_bq = 1.02 * 5.9604644775390625e-08 * b;
+    }
+    __syncthreads();
+    const double bq = *s_bq;
+
+    unsigned long long n_cand = 0;
+    int it = 0;
+    for (int p = s; p < a.w; p += a.nsplit, ++it) {
+        const int cur = it & 1;
+        float *lut = cur ? lut1 : lut0;
+        const int l = pr[p];
+        if (tid == 0 && p + a.nsplit < a.w) {
+            // the other buffer was last read in iteration it-1, which ended with a barrier
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bars[cur ^ 1], t1_bytes);
+            tma_load_1d(cur ? lut0 : lut1, a.T1 + (int64_t)pr[p + a.nsplit] * nent, t1_bytes, &bars[cur ^ 1]);
+        }
+        const int64_t start = a.list_off[l];
+        const int len = a.list_len[l];  // 0 for lists another shard owns: nothing to build or scan
+        // s[j] = sum_t q_t (q_t - 2 C_l,t) over the (permuted) sub-vector j, binary64
+        if (tid < M && len > 0) {
+            const double *Cl = a.C + (int64_t)l * a.d;
+            double acc = 0.0;
+            for (int t = 0; t < S; ++t) {
+                int src = tid * S + t;
+                if (a.perm) src = a.perm[src];
+                const double qt = qv[src];
+                acc += qt * (qt - 2.0 * Cl[src]);
+            }
+            sj[tid] = acc;
+        }
+        __syncthreads();
+        mbar_wait(&bars[cur], (uint32_t)((it >> 1) & 1));
+        // LUT in place: lut = T1[l] + T2 + s
+        if (len > 0)
+            for (int e = tid; e < nent; e += MMIDX_NT) lut[e] = (lut[e] + t2[e]) + __double2float_rn(sj[e / ks]);
+        const uint8_t *lc = a.codes + start * M;
+        constexpr int ROUND = TopK32<CAP32>::ROUND;
+        for (int base = 0; base < len; base += ROUND) {
+            c32.maybe_compact(a.k, bq, rel);  // contains the round barrier (also publishes the LUT on round 0)
+            const float thr32 = c32.thr32;
+            constexpr int CPT = (M == 8) ? 2 : 1;  // candidates per 128-bit load
+#pragma unroll
+            for (int e = 0; e < ROUND / (MMIDX_NT * CPT); ++e) {
+                const int i0 = base + (e * MMIDX_NT + tid) * CPT;
+                uint4 c = make_uint4(0, 0, 0, 0);
+                if (i0 < len) c = ld_nc_u4(lc + (int64_t)i0 * M);
+                if (M == 8) {
+                    float d0 = lut[c.x & 255u];
+                    float d1 = lut[c.z & 255u];
+                    d0 += lut[256 + ((c.x >> 8) & 255u)];
+                    d1 += lut[256 + ((c.z >> 8) & 255u)];
+                    d0 += lut[512 + ((c.x >> 16) & 255u)];
+                    d1 += lut[512 + ((c.z >> 16) & 255u)];
+                    d0 += lut[768 + (c.x >> 24)];
+                    d1 += lut[768 + (c.z >> 24)];
+                    d0 += lut[1024 + (c.y & 255u)];
+                    d1 += lut[1024 + (c.w & 255u)];
+                    d0 += lut[1280 + ((c.y >> 8) & 255u)];
+                    d1 += lut[1280 + ((c.w >> 8) & 255u)];
+                    d0 += lut[1536 + ((c.y >> 16) & 255u)];
+                    d1 += lut[1536 + ((c.w >> 16) & 255u)];
+                    d0 += lut[1792 + (c.y >> 24)];
+                    d1 += lut[1792 + (c.w >> 24)];
+                    c32.push((i0 < len) && d0 <= thr32, d0, (int)(start + i0), p);
+                    c32.push((i0 + 1 < len) && d1 <= thr32, d1, (int)(start + i0 + 1), p);
+                } else {
+                    const uint32_t wds[4] = {c.x, c.y, c.z, c.w};
+                    float d0 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) d0 += lut[j * 256 + ((wds[j >> 2] >> ((j & 3) * 8)) & 255u)];
+                    c32.push((i0 < len) && d0 <= thr32, d0, (int)(start + i0), p);
+                }
+            }
+        }
+        n_cand += (unsigned long long)len;
+        __syncthreads();  // all reads of `lut` done before it is refilled two iterations later
+    }
+
+    // ---- final phase: shrink to the error band, evaluate the survivors exactly, exact top-k ----
+    __syncthreads();
+    const int n_before = c32.cnt;
+    if (n_before > a.k) c32.compact(a.k, bq, rel);
+    const int nsurv = c32.cnt;
+    const bool overflow = c32.overflow != 0;
+    TopK<ECAP> &tk = *reinterpret_cast<TopK<ECAP> *>(regA);  // aliases t2/lut: no TMA is in flight any more
+    double *xs = reinterpret_cast<double *>(regA + tk_bytes) + (size_t)(tid >> 5) * M * (S + 1);
+    tk.init();
+    if (!overflow) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int base = 0; base < nsurv; base += MMIDX_NT / 32) {
+            const int e = base + warp;  // warp-uniform
+            double dv = 0.0;
+            unsigned long long sq = 0ull;
+            int pay = 0;
+            if (e < nsurv) {
+                const int ps = c32.pos[e], pb = c32.probe[e];
+                const int l = pr[pb];
+                dv = exact_adc_warp(a.C + (int64_t)l * a.d, qv, a.perm, a.P, a.codes + (int64_t)ps * M, M, ks, S, xs);
+                sq = (((unsigned long long)pb) << 32) | (unsigned long long)(ps - a.list_off[l]);
+                pay = a.iids[ps];
+            }
+            tk.push(e < nsurv && lane == 0, dv, sq, pay);
+        }
+    }
+    if (a.stats && tid == 0) {
+        atomicAdd(&a.stats[0], n_cand);
+        atomicAdd(&a.stats[2], (unsigned long long)nsurv);
+        if (overflow) atomicAdd(&a.stats[3], 1ull);
+    }
+    if (overflow && tid == 0) {
+        const int slot = atomicAdd(a.fb_count, 1);
+        a.fb_list[slot] = (int32_t)(q * a.nsplit + s);
+    }
+    // on overflow an empty result is written here and the direct kernel overwrites it
+    write_result(tk, o, q, s, a.k, -1.0);
+}
+
+// Direct (table-free) exact scan for the rare items the fast kernel could not finish: every candidate of the
+// item's probes is evaluated in binary64 from the quantizers.  grid: any; CTAs stride over fb_list.
+template <int CAP>
+__global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_direct(FastArgs a, TopkOut o) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TopK<CAP> &tk = *reinterpret_cast<TopK<CAP> *>(smem_raw);
+    constexpr int ROUND = TopK<CAP>::ROUND;
+    const int nfb = *a.fb_count;
+    for (int fi = blockIdx.x; fi < nfb; fi += gridDim.x) {
+        const int item = a.fb_list[fi];
+        const int64_t q = item / a.nsplit;
+        const int s = item - (int)q * a.nsplit;
+        const int32_t *pr = a.probes + q * a.w;
+        const double *qv = a.Q + q * (int64_t)a.d;
+        __syncthreads();
+        tk.init();
+        for (int p = s; p < a.w; p += a.nsplit) {
+            const int l = pr[p];
+            const int64_t start = a.list_off[l];
+            const int len = a.list_len[l];
+            const double *Cl = a.C + (int64_t)l * a.d;
+            for (int base = 0; base < len; base += ROUND) {
+                tk.maybe_compact(a.k);
+                const double thr = tk.thr;
+                const bool strict = tk.strict != 0;
+                for (int e = 0; e < ROUND / MMIDX_NT; ++e) {
+                    const int i = base + e * MMIDX_NT + threadIdx.x;
+                    const bool valid = i < len;
+                    double dv = 0.0;
+                    if (valid) dv = exact_adc(Cl, qv, a.perm, a.P, a.codes + (start + i) * a.m, a.m, a.ks, a.S);
+                    const bool pred = valid && (dv < thr || (dv == thr && !strict));
+                    tk.push(pred, dv, (((unsigned long long)p) << 32) | (unsigned long long)i, pred ? a.iids[start + i] : 0);
+                }
+            }
+        }
+        write_result(tk, o, q, s, a.k, -1.0);
+    }
+}
+
+// tie pass collector without ADC tables in memory: exact distances straight from the quantizers.
+struct TieDirectArgs {
+    const double *Q, *C, *P;
+    const int32_t *perm;
+    const int32_t *probes;
+    const uint8_t *codes;
+    const int32_t *iids;
+    const int64_t *list_off;
+    const int32_t *list_len;
+    int d, m, ks, S, w, k, code_bytes;
+};
+
+__global__ void __launch_bounds__(MMIDX_NT) k_tie_collect_ivfpq_direct(TieDirectArgs a, const double *__restrict__ res_dist,
+                                                                       const int32_t *__restrict__ amb_list,
+                                                                       const int32_t *__restrict__ amb_count, TieLists o) {
+    __shared__ int warp_sums[MMIDX_NT / 32];
+    const int na = *amb_count;
+    for (int ai = blockIdx.x; ai < na; ai += gridDim.x) {
+        const int64_t q = amb_list[ai];
+        const double T = res_dist[q * a.k + a.k - 1];
+        const double *qv = a.Q + q * (int64_t)a.d;
+        int found = 0;
+        for (int p = 0; p < a.w && found < a.k; ++p) {
+            const int l = a.probes[q * a.w + p];
+            const int64_t start = a.list_off[l];
+            const double *Cl = a.C + (int64_t)l * a.d;
+            const uint8_t *cp = a.codes + start * a.code_bytes;
+            const int32_t *li = a.iids + start;
+            const TieDirectArgs &r = a;
+            tie_sweep(a.list_len[l], ((unsigned long long)p) << 32, T, a.k, found, warp_sums, o, q,
+                      [=](int64_t i) { return exact_adc(Cl, qv, r.perm, r.P, cp + i * r.code_bytes, r.m, r.ks, r.S); },
+                      [li](int64_t i) { return li[i]; });
+        }
+        if (threadIdx.x == 0) o.cnt[q] = min(found, a.k);
+        __syncthreads();
+    }
+}
+
+}  // namespace mmidx

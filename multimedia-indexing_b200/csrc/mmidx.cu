@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "tie_resolve.cuh"
+#include "fast_scan.cuh"
 
 using namespace mmidx;
 
@@ -151,6 +152,11 @@ struct mmidx_index {
     std::mutex mu;
     StageTimer timer;
     int last_launches = 0;
+    // fast path tables (fast_scan.cuh), rebuilt when a quantizer or the permutation changes
+    DevBuf dT1, dP32t, dt1max, dpmax, dstats;
+    bool fast_ready = false;
+    bool force_exact = false;  // MMIDX_MODE=exact
+    bool want_stats = false;   // MMIDX_STATS=1
     size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
 };
 
@@ -234,6 +240,8 @@ extern "C" int mmidx_create(const mmidx_params *pp, mmidx_t **out) {
         delete ix;
         return fail(MMIDX_ERR_INVALID, "shard_rank out of range");
     }
+    if (const char *e = getenv("MMIDX_MODE")) ix->force_exact = strcmp(e, "exact") == 0;
+    if (const char *e = getenv("MMIDX_STATS")) ix->want_stats = atoi(e) != 0;
     if (const char *e = getenv("MMIDX_LUT_CHUNK_MB")) {
         long v = atol(e);
         if (v >= 1) ix->lut_chunk_bytes = (size_t)v << 20;
@@ -261,6 +269,12 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
     if (!ix) return MMIDX_OK;
     {
         DeviceGuard g(ix->device);
+        if (ix->want_stats && ix->dstats.p) {  // MMIDX_STATS=1: debug counters of the fast scan kernel
+            unsigned long long h[4] = {0, 0, 0, 0};
+            cudaDeviceSynchronize();
+            cudaMemcpy(h, ix->dstats.p, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[mmidx stats] candidates=%llu filter_passes=%llu exact_accepts=%llu\n", h[0], h[1], h[2]);
+        }
         if (ix->stream) {
             cudaStreamSynchronize(ix->stream);
             cudaStreamDestroy(ix->stream);
@@ -288,6 +302,7 @@ extern "C" int mmidx_set_product_quantizer(mmidx_t *ix, const double *P) {
     CK(cudaMemcpyAsync(ix->dP.p, P, bytes, cudaMemcpyHostToDevice, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
     ix->has_P = true;
+    ix->fast_ready = false;
     return MMIDX_OK;
 }
 
@@ -305,6 +320,7 @@ extern "C" int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C) {
     RET(post_launch("k_transpose", nullptr));
     CK(cudaStreamSynchronize(ix->stream));
     ix->has_C = true;
+    ix->fast_ready = false;
     return MMIDX_OK;
 }
 
@@ -313,6 +329,7 @@ extern "C" int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm) {
     if (ix->p.type == MMIDX_LINEAR) return fail(MMIDX_ERR_INVALID, "Linear index takes no transformation");
     DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lk(ix->mu);
+    ix->fast_ready = false;
     if (!perm) {
         ix->has_perm = false;
         return MMIDX_OK;
@@ -996,6 +1013,177 @@ static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, co
     return MMIDX_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// fast path (fast_scan.cuh): fp32 filter + exact verification, no ADC tables in HBM
+// ---------------------------------------------------------------------------------------------------------
+static bool fast_eligible(const mmidx_index *ix) {
+    if (ix->p.type != MMIDX_IVFPQ || ix->force_exact) return false;
+    if (ix->p.ks > 256 || (ix->p.m != 8 && ix->p.m != 16)) return false;
+    if (((int64_t)ix->p.m * ix->p.ks) % 4 != 0) return false;
+    return true;
+}
+
+static int prepare_fast(mmidx_index *ix) {
+    if (ix->fast_ready) return MMIDX_OK;
+    cudaStream_t st = ix->stream;
+    const int m = ix->p.m, ks = ix->p.ks, S = ix->S, nlist = ix->p.nlist, d = ix->p.d;
+    RET(ix->dT1.reserve(sizeof(float) * (size_t)nlist * m * ks, 0, st));
+    RET(ix->dP32t.reserve(sizeof(float) * (size_t)m * ks * S, 0, st));
+    RET(ix->dt1max.reserve(sizeof(float) * (size_t)nlist * m, 0, st));
+    RET(ix->dpmax.reserve(sizeof(float) * (size_t)m, 0, st));
+    RET(ix->dstats.reserve(sizeof(unsigned long long) * 4, 0, st));
+    CK(cudaMemsetAsync(ix->dt1max.p, 0, sizeof(float) * (size_t)nlist * m, st));
+    CK(cudaMemsetAsync(ix->dpmax.p, 0, sizeof(float) * (size_t)m, st));
+    CK(cudaMemsetAsync(ix->dstats.p, 0, sizeof(unsigned long long) * 4, st));
+    const int32_t *perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
+    k_build_t1<<<dim3(nlist, m), MMIDX_NT, sizeof(double) * (size_t)S, st>>>(ix->dC.as<double>(), ix->dP.as<double>(), perm, d, m,
+                                                                          ks, S, ix->dT1.as<float>(), ix->dt1max.as<float>());
+    RET(post_launch("k_build_t1", nullptr));
+    k_build_p32t<<<m, MMIDX_NT, 0, st>>>(ix->dP.as<double>(), m, ks, S, ix->dP32t.as<float>(), ix->dpmax.as<float>());
+    RET(post_launch("k_build_p32t", nullptr));
+    CK(cudaStreamSynchronize(st));
+    ix->fast_ready = true;
+    return MMIDX_OK;
+}
+
+template <int CAP32, int M>
+static size_t fast_smem_bytes(int ks, int S, int d) {
+    constexpr int ECAP = FastExactCap<CAP32>::value;
+    const size_t c32b = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
+    const size_t tkb = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
+    const size_t xsb = (size_t)(MMIDX_NT / 32) * M * (S + 1) * sizeof(double);
+    size_t regA = std::max((size_t)3 * M * ks * sizeof(float), tkb + xsb);
+    regA = (regA + 15) & ~(size_t)15;
+    return c32b + regA + (size_t)d * 8 + 2 * (size_t)M * 8 + ((size_t)M + (M & 1)) * 4 + 16 + 8 + 64;
+}
+
+template <int CAP32, int M>
+static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k, int w, const ResultBufs &res,
+                            double *res_tie, int32_t *amb_list, int32_t *amb_count, bool resolve_ties, cudaStream_t st,
+                            int *launches) {
+    Scratch sc(st);
+    int32_t *dprobes;
+    RET(sc.get(&dprobes, (size_t)nq * w));
+    {
+        StageMark sm(ix, st, 0);
+        RET(coarse_probe_dev(ix, dQ, nq, w, dprobes, sc, st, launches));
+    }
+    int nsplit = (int)std::min<int64_t>(w, std::max<int64_t>(1, (148 * 4 + nq - 1) / nq));
+    FastArgs a{};
+    a.Q = dQ;
+    a.C = ix->dC.as<double>();
+    a.P = ix->dP.as<double>();
+    a.T1 = ix->dT1.as<float>();
+    a.P32t = ix->dP32t.as<float>();
+    a.t1max = ix->dt1max.as<float>();
+    a.pmax = ix->dpmax.as<float>();
+    a.perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
+    a.probes = dprobes;
+    a.codes = ix->csr_codes.as<uint8_t>();
+    a.iids = ix->csr_iids.as<int32_t>();
+    a.list_off = ix->dlist_off.as<int64_t>();
+    a.list_len = ix->dlist_len.as<int32_t>();
+    a.d = ix->p.d;
+    a.m = M;
+    a.ks = ix->p.ks;
+    a.S = ix->S;
+    a.w = w;
+    a.k = k;
+    a.nsplit = nsplit;
+    a.stats = ix->want_stats ? ix->dstats.as<unsigned long long>() : nullptr;
+    RET(sc.get(&a.fb_list, (size_t)nq * nsplit));
+    RET(sc.get(&a.fb_count, 1));
+    CK(cudaMemsetAsync(a.fb_count, 0, sizeof(int32_t), st));
+    const size_t smem = fast_smem_bytes<CAP32, M>(ix->p.ks, ix->S, ix->p.d);
+    RET(set_smem(k_ivfpq_scan_fast<CAP32, M>, smem));
+    TopkOut o{};
+    o.nparts = nsplit;
+    if (nsplit == 1) {
+        o.iids = res.iids;
+        o.dist = res.dist;
+        o.seq = res.seq;
+        o.cnt = res.cnt;
+        o.tie = res_tie;
+        o.amb_list = amb_list;
+        o.amb_count = amb_count;
+    } else {
+        unsigned long long *pseq;
+        RET(sc.get(&o.iids, (size_t)nq * nsplit * k));
+        RET(sc.get(&o.dist, (size_t)nq * nsplit * k));
+        RET(sc.get(&pseq, (size_t)nq * nsplit * k));
+        o.seq = pseq;
+        RET(sc.get(&o.cnt, (size_t)nq * nsplit));
+        RET(sc.get(&o.tie, (size_t)nq * nsplit));
+    }
+    {
+        StageMark sm(ix, st, 2);
+        k_ivfpq_scan_fast<CAP32, M><<<dim3(nsplit, (unsigned)nq), MMIDX_NT, smem, st>>>(a, o);
+        RET(post_launch("k_ivfpq_scan_fast", launches));
+    }
+    StageMark sm3(ix, st, 3);
+    {
+        // items whose error band overflowed the fp32 collector (massive exact duplicates): table-free exact scan
+        constexpr int DCAP = (CAP32 <= 1024) ? 1024 : 2048;
+        const size_t dsmem = topk_bytes<DCAP>();
+        RET(set_smem(k_ivfpq_scan_direct<DCAP>, dsmem));
+        const int dg = (int)std::min<int64_t>(nq * nsplit, 296);
+        k_ivfpq_scan_direct<DCAP><<<dg, MMIDX_NT, dsmem, st>>>(a, o);
+        RET(post_launch("k_ivfpq_scan_direct", launches));
+    }
+    if (nsplit > 1) {
+        if (cap_for(k) == 2048)
+            RET(launch_merge<2048>(o, nsplit, nq, k, res, amb_list, amb_count, res_tie, 1, nsplit, st, launches));
+        else
+            RET(launch_merge<1024>(o, nsplit, nq, k, res, amb_list, amb_count, res_tie, 1, nsplit, st, launches));
+    }
+    if (resolve_ties) {
+        TieLists tl;
+        RET(sc.get(&tl.seq, (size_t)nq * k));
+        RET(sc.get(&tl.pay, (size_t)nq * k));
+        RET(sc.get(&tl.eq, (size_t)nq * k));
+        RET(sc.get(&tl.cnt, (size_t)nq));
+        TieDirectArgs t{};
+        t.Q = dQ;
+        t.C = a.C;
+        t.P = a.P;
+        t.perm = a.perm;
+        t.probes = dprobes;
+        t.codes = a.codes;
+        t.iids = a.iids;
+        t.list_off = a.list_off;
+        t.list_len = a.list_len;
+        t.d = a.d;
+        t.m = M;
+        t.ks = a.ks;
+        t.S = a.S;
+        t.w = w;
+        t.k = k;
+        t.code_bytes = ix->code_bytes;
+        const int tg = (int)std::min<int64_t>(nq, 296);
+        k_tie_collect_ivfpq_direct<<<tg, MMIDX_NT, 0, st>>>(t, res.dist, amb_list, amb_count, tl);
+        RET(post_launch("k_tie_collect_ivfpq_direct", launches));
+        k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count,
+                                                           res.iids, res.dist, res.seq);
+        RET(post_launch("k_tie_finish", launches));
+    }
+    return MMIDX_OK;
+}
+
+static int ivfpq_chunk_fast_dispatch(mmidx_index *ix, const double *dQ, int64_t nq, int k, int w, const ResultBufs &res,
+                                     double *res_tie, int32_t *amb_list, int32_t *amb_count, bool resolve_ties,
+                                     cudaStream_t st, int *launches) {
+#define FASTCALL(CAPV, MV) \
+    return ivfpq_chunk_fast<CAPV, MV>(ix, dQ, nq, k, w, res, res_tie, amb_list, amb_count, resolve_ties, st, launches)
+    if (ix->p.m == 8) {
+        if (k <= 256) FASTCALL(1024, 8);
+        FASTCALL(2048, 8);
+    } else {
+        if (k <= 256) FASTCALL(1024, 16);
+        FASTCALL(2048, 16);
+    }
+#undef FASTCALL
+}
+
 static int validate_search(mmidx_index *ix, int64_t nq, int k, int *w_out) {
     if (nq < 0) return fail(MMIDX_ERR_INVALID, "nq < 0");
     if (k < 1) return fail(MMIDX_ERR_INVALID, "k must be >= 1 (BoundedPriorityQueue max size)");
@@ -1021,6 +1209,11 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(seal(ix));
     }
+    const bool fast = fast_eligible(ix) && k <= 512;  // larger k: exact ADC-table kernels
+    if (fast && !ix->fast_ready) {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        RET(prepare_fast(ix));
+    }
     int launches = 0;
     ix->timer.reset();
     StageMark whole(ix, st, 4);
@@ -1028,7 +1221,10 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
     int32_t *amb_list, *amb_count;
     const int d = ix->p.d;
     int64_t qchunk = nq;
-    if (ix->p.type == MMIDX_IVFPQ) {
+    if (ix->p.type == MMIDX_IVFPQ && fast) {
+        // scratch is the coarse distance matrix only: [nq][nlist] binary64, bounded to 1 GiB
+        qchunk = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / ((size_t)ix->p.nlist * sizeof(double))));
+    } else if (ix->p.type == MMIDX_IVFPQ) {
         size_t per_q = (size_t)w * ix->p.m * ix->p.ks * sizeof(double);
         qchunk = std::max<int64_t>(1, (int64_t)(ix->lut_chunk_bytes / per_q));
     } else if (ix->p.type == MMIDX_PQ) {
@@ -1050,6 +1246,11 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
         const bool big = cap_for(k) == 2048;
         switch (ix->p.type) {
             case MMIDX_IVFPQ:
+                if (fast) {
+                    r = ivfpq_chunk_fast_dispatch(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count,
+                                                  !sharded, st, &launches);
+                    break;
+                }
                 r = big ? ivfpq_chunk<2048>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches)
                         : ivfpq_chunk<1024>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches);
                 break;

@@ -99,8 +99,12 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("mode", ["fast", "exact"])
 @pytest.mark.parametrize("case", CASES)
-def test_ivfpq_vs_oracle(case):
+def test_ivfpq_vs_oracle(case, mode, monkeypatch):
+    # "fast": fused fp32-filter + exact-verify kernel where the geometry allows it (ks <= 256, m in {8, 16});
+    # "exact": MMIDX_MODE=exact forces the binary64 ADC-table kernels for every geometry.  Same bits either way.
+    monkeypatch.setenv("MMIDX_MODE", mode)
     d, m, ks, nlist, w, n, nq, k, use_perm = case
     ce = synth.mixture_centers(d, 64)
     X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
@@ -288,7 +292,13 @@ def test_full_size_config3_properties():
     assert (one[0][0] == iids[5]).all() and (one[1][0] == dist[5]).all()
 
 
-def test_large_batch_single_split_path():
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_large_batch_single_split_path(mode, monkeypatch):
+    monkeypatch.setenv("MMIDX_MODE", mode)
+    _large_batch_single_split_path()
+
+
+def _large_batch_single_split_path():
     """>= 592 queries in one chunk -> one CTA per query (nsplit == 1) and large select/merge grids.  Regression:
     TopK::init() lacked a barrier, so a CTA could act on a previous CTA's shared-memory garbage."""
     d, m, ks, nlist, w, n, nq, k = 64, 8, 256, 256, 16, 60000, 3000, 100
@@ -303,3 +313,23 @@ def test_large_batch_single_split_path():
     ref = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=O.num_threads())
     for _ in range(2):
         assert_same(ix.searchBatch(k, Q), ref, "nsplit=1")
+
+
+def test_fast_path_overflow_falls_back_to_direct_kernel():
+    """More exact duplicates than the fp32 collector can keep inside its error band (> 512 equal distances):
+    the fast kernel hands the query to the table-free exact kernel and the tie pass; results must still follow the
+    queue rules bit for bit."""
+    rng = np.random.default_rng(11)
+    d, m, ks, nlist, w, k = 64, 8, 256, 8, 8, 50
+    base = np.clip(np.rint(rng.normal(64, 20, size=(5, d))), 0, 255)
+    X = np.vstack([base[rng.integers(0, 5, size=6000)], np.clip(np.rint(rng.normal(64, 20, size=(500, d))), 0, 255)])
+    X = X[rng.permutation(len(X))]
+    Q = np.vstack([base + 1.0, np.clip(np.rint(rng.normal(64, 20, size=(11, d))), 0, 255)])
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=3000, iters=3, centers=np.vstack([base, base + 40.0]))
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    ref = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w)
+    assert_same(ix.searchBatch(k, Q), ref, "overflow -> direct")
+    big = np.vstack([Q] * 60)  # > 592 queries: one CTA per query
+    assert_same(ix.searchBatch(k, big), tuple(np.concatenate([r] * 60) for r in ref), "overflow -> direct, nsplit=1")
