@@ -73,6 +73,106 @@ __global__ void __launch_bounds__(MMIDX_NT) k_build_p32t(const double *__restric
     atomicMax(reinterpret_cast<int *>(&pmax[j]), __float_as_int(mx));
 }
 
+// ---- bank-conflict-aware order inside an inverted list ------------------------------------------------
+// The scan's cost is shared-memory wavefronts: one warp-wide lookup into sub-table j takes as many cycles as
+// the most loaded bank has DISTINCT addresses (bank = code % 32 for fp32 entries).  Order inside a list is free
+// (the queue's offer order is carried separately as `orank`), so each list is re-ordered greedily, in chunks of
+// RCH entries, such that the 32 codes one warp instruction touches spread over the banks: pick by pick, the
+// entry that adds the least sum_j (2*load_j[bank]+1) over sub-quantizers whose address is not yet in the group.
+// M == 8: a thread scans two adjacent codes per 128-bit load, so a warp instruction covers the even (then the
+// odd) positions of a 64-entry block; M == 16: 32 consecutive positions.  grid nlist; src[] is list-relative.
+constexpr int RCH = 512;
+
+template <int M>
+__global__ void __launch_bounds__(MMIDX_NT) k_reorder_lists(const uint8_t *__restrict__ codes, const int64_t *__restrict__ list_off,
+                                                            const int32_t *__restrict__ list_len, int32_t *__restrict__ src) {
+    __shared__ uint8_t cs[RCH][M];
+    __shared__ int load[M][32];
+    __shared__ unsigned seen[M][8];
+    __shared__ unsigned red[MMIDX_NT / 32];
+    __shared__ unsigned s_win;
+    constexpr int BLK = (M == 8) ? 64 : 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l = blockIdx.x;
+    const int64_t start = list_off[l];
+    const int len = list_len[l];
+    for (int cb = 0; cb < len; cb += RCH) {
+        const int n = min(RCH, len - cb);
+        __syncthreads();
+        for (int e = tid; e < n * M; e += MMIDX_NT) cs[e / M][e % M] = codes[(start + cb) * M + e];
+        bool alive[RCH / MMIDX_NT];
+#pragma unroll
+        for (int r = 0; r < RCH / MMIDX_NT; ++r) alive[r] = (tid + r * MMIDX_NT) < n;
+        for (int bb = 0; bb < n; bb += BLK) {
+            const int rblk = min(BLK, n - bb);
+            for (int h = 0; h < BLK / 32; ++h) {
+                const int gsize = (M == 8) ? ((h == 0) ? (rblk + 1) / 2 : rblk / 2) : rblk;
+                __syncthreads();
+                for (int e = tid; e < M * 32; e += MMIDX_NT) (&load[0][0])[e] = 0;
+                for (int e = tid; e < M * 8; e += MMIDX_NT) (&seen[0][0])[e] = 0u;
+                for (int t = 0; t < gsize; ++t) {
+                    __syncthreads();
+                    unsigned best = 0xffffffffu;
+#pragma unroll
+                    for (int r = 0; r < RCH / MMIDX_NT; ++r) {
+                        if (alive[r]) {
+                            const int idx = tid + r * MMIDX_NT;
+                            int cost = 0;
+#pragma unroll
+                            for (int j = 0; j < M; ++j) {
+                                const unsigned c = cs[idx][j];
+                                const bool dup = (seen[j][c >> 5] >> (c & 31u)) & 1u;
+                                cost += dup ? 0 : 2 * load[j][c & 31u] + 1;
+                            }
+                            best = min(best, ((unsigned)cost << 16) | (unsigned)idx);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if (lane == 0) red[warp] = best;
+                    __syncthreads();
+                    if (tid == 0) {
+                        unsigned b = red[0];
+                        for (int wv = 1; wv < MMIDX_NT / 32; ++wv) b = min(b, red[wv]);
+                        s_win = b;
+                        const int idx = (int)(b & 0xffffu);
+                        const int pos = (M == 8) ? (bb + 2 * t + h) : (bb + t);
+                        src[start + cb + pos] = cb + idx;
+                        for (int j = 0; j < M; ++j) {
+                            const unsigned c = cs[idx][j];
+                            if (!((seen[j][c >> 5] >> (c & 31u)) & 1u)) {
+                                seen[j][c >> 5] |= 1u << (c & 31u);
+                                load[j][c & 31u] += 1;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const int widx = (int)(s_win & 0xffffu);
+#pragma unroll
+                    for (int r = 0; r < RCH / MMIDX_NT; ++r)
+                        if (widx == tid + r * MMIDX_NT) alive[r] = false;
+                }
+            }
+        }
+    }
+}
+
+// apply the order: ocodes/oiids/orank[start + i] = codes/iids/rank of insertion entry src[start + i]
+__global__ void k_apply_order(const uint8_t *__restrict__ codes, const int32_t *__restrict__ iids,
+                              const int64_t *__restrict__ list_off, const int32_t *__restrict__ list_len,
+                              const int32_t *__restrict__ src, int m, uint8_t *__restrict__ ocodes,
+                              int32_t *__restrict__ oiids, int32_t *__restrict__ orank) {
+    const int l = blockIdx.x;
+    const int64_t start = list_off[l];
+    const int len = list_len[l];
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const int s = src[start + i];
+        for (int b = 0; b < m; ++b) ocodes[(start + i) * m + b] = codes[(start + s) * m + b];
+        oiids[start + i] = iids[start + s];
+        orank[start + i] = s;
+    }
+}
+
 struct FastArgs {
     const double *Q;          // [nq][d]
     const double *C;          // [nlist][d]
@@ -83,8 +183,11 @@ struct FastArgs {
     const float *pmax;        // [m]
     const int32_t *perm;      // [d] or NULL
     const int32_t *probes;    // [nq][w]
-    const uint8_t *codes;     // CSR
+    const uint8_t *codes;     // CSR, insertion order (direct kernel, tie pass)
     const int32_t *iids;
+    const uint8_t *ocodes;    // CSR, bank-conflict-aware order inside each list (k_reorder_lists); fast kernel only
+    const int32_t *oiids;
+    const int32_t *orank;     // insertion rank (= offer order inside the list) of every reordered entry
     const int64_t *list_off;
     const int32_t *list_len;
     int d, m, ks, S, w, k, nsplit;
@@ -101,6 +204,16 @@ __device__ __forceinline__ unsigned f32_key(float f) {
 __device__ __forceinline__ float f32_unkey(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
+
+// shared-memory gather with a compile-time offset: address = base + 4*byte, one LEA + one LDS per lookup
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+// ADC table entry of sub-quantizer J for byte I of a packed code word (ks == 256: 1 KiB per sub-table)
+#define MMIDX_LK(J, word, I) lds_f32<(J) * 1024>(lb + (__byte_perm((word), 0, 0x4440 | (I)) << 2))
 
 // CTA-wide collector on fp32 keys with an error-band slack (see the header comment).
 template <int CAP>
@@ -290,12 +403,12 @@ __device__ __forceinline__ double exact_adc_warp(const double *__restrict__ Cl, 
 
 template <int CAP32>
 struct FastExactCap {
-    static constexpr int value = (CAP32 / 2 <= 512) ? 512 : CAP32 / 2;  // exact collector holds the survivors
+    static constexpr int value = 512;  // exact collector for the survivors; more survivors than this -> direct kernel
 };
 
 // grid (nsplit, nq).  CTA (s, q) handles probes s, s+nsplit, ... of query q in rank order.
 template <int CAP32, int M>
-__global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
+__global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
     constexpr int ECAP = FastExactCap<CAP32>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TopK32<CAP32> &c32 = *reinterpret_cast<TopK32<CAP32> *>(smem_raw);
@@ -414,7 +527,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_fast(FastArgs a, TopkOu
         // LUT in place: lut = T1[l] + T2 + s
         if (len > 0)
             for (int e = tid; e < nent; e += MMIDX_NT) lut[e] = (lut[e] + t2[e]) + __double2float_rn(sj[e / ks]);
-        const uint8_t *lc = a.codes + start * M;
+        const uint8_t *lc = a.ocodes + start * M;
+        const uint32_t lb = smem_u32(lut);
         constexpr int ROUND = TopK32<CAP32>::ROUND;
         for (int base = 0; base < len; base += ROUND) {
             c32.maybe_compact(a.k, bq, rel);  // contains the round barrier (also publishes the LUT on round 0)
@@ -422,33 +536,48 @@ __global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_fast(FastArgs a, TopkOu
             constexpr int CPT = (M == 8) ? 2 : 1;  // candidates per 128-bit load
 #pragma unroll
             for (int e = 0; e < ROUND / (MMIDX_NT * CPT); ++e) {
+                // warp-uniform skip of the list tail (push() only synchronises within the warp)
+                if (base + (e * MMIDX_NT + (tid & ~31)) * CPT >= len) continue;
                 const int i0 = base + (e * MMIDX_NT + tid) * CPT;
                 uint4 c = make_uint4(0, 0, 0, 0);
                 if (i0 < len) c = ld_nc_u4(lc + (int64_t)i0 * M);
                 if (M == 8) {
-                    float d0 = lut[c.x & 255u];
-                    float d1 = lut[c.z & 255u];
-                    d0 += lut[256 + ((c.x >> 8) & 255u)];
-                    d1 += lut[256 + ((c.z >> 8) & 255u)];
-                    d0 += lut[512 + ((c.x >> 16) & 255u)];
-                    d1 += lut[512 + ((c.z >> 16) & 255u)];
-                    d0 += lut[768 + (c.x >> 24)];
-                    d1 += lut[768 + (c.z >> 24)];
-                    d0 += lut[1024 + (c.y & 255u)];
-                    d1 += lut[1024 + (c.w & 255u)];
-                    d0 += lut[1280 + ((c.y >> 8) & 255u)];
-                    d1 += lut[1280 + ((c.w >> 8) & 255u)];
-                    d0 += lut[1536 + ((c.y >> 16) & 255u)];
-                    d1 += lut[1536 + ((c.w >> 16) & 255u)];
-                    d0 += lut[1792 + (c.y >> 24)];
-                    d1 += lut[1792 + (c.w >> 24)];
+                    float d0 = MMIDX_LK(0, c.x, 0);
+                    float d1 = MMIDX_LK(0, c.z, 0);
+                    d0 += MMIDX_LK(1, c.x, 1);
+                    d1 += MMIDX_LK(1, c.z, 1);
+                    d0 += MMIDX_LK(2, c.x, 2);
+                    d1 += MMIDX_LK(2, c.z, 2);
+                    d0 += MMIDX_LK(3, c.x, 3);
+                    d1 += MMIDX_LK(3, c.z, 3);
+                    d0 += MMIDX_LK(4, c.y, 0);
+                    d1 += MMIDX_LK(4, c.w, 0);
+                    d0 += MMIDX_LK(5, c.y, 1);
+                    d1 += MMIDX_LK(5, c.w, 1);
+                    d0 += MMIDX_LK(6, c.y, 2);
+                    d1 += MMIDX_LK(6, c.w, 2);
+                    d0 += MMIDX_LK(7, c.y, 3);
+                    d1 += MMIDX_LK(7, c.w, 3);
                     c32.push((i0 < len) && d0 <= thr32, d0, (int)(start + i0), p);
                     c32.push((i0 + 1 < len) && d1 <= thr32, d1, (int)(start + i0 + 1), p);
                 } else {
-                    const uint32_t wds[4] = {c.x, c.y, c.z, c.w};
-                    float d0 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) d0 += lut[j * 256 + ((wds[j >> 2] >> ((j & 3) * 8)) & 255u)];
+                    float d0 = MMIDX_LK(0, c.x, 0);
+                    float d1 = MMIDX_LK(1, c.x, 1);
+                    d0 += MMIDX_LK(2, c.x, 2);
+                    d1 += MMIDX_LK(3, c.x, 3);
+                    d0 += MMIDX_LK(4, c.y, 0);
+                    d1 += MMIDX_LK(5, c.y, 1);
+                    d0 += MMIDX_LK(6, c.y, 2);
+                    d1 += MMIDX_LK(7, c.y, 3);
+                    d0 += MMIDX_LK(8, c.z, 0);
+                    d1 += MMIDX_LK(9, c.z, 1);
+                    d0 += MMIDX_LK(10, c.z, 2);
+                    d1 += MMIDX_LK(11, c.z, 3);
+                    d0 += MMIDX_LK(12, c.w, 0);
+                    d1 += MMIDX_LK(13, c.w, 1);
+                    d0 += MMIDX_LK(14, c.w, 2);
+                    d1 += MMIDX_LK(15, c.w, 3);
+                    d0 += d1;
                     c32.push((i0 < len) && d0 <= thr32, d0, (int)(start + i0), p);
                 }
             }
@@ -462,7 +591,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_fast(FastArgs a, TopkOu
     const int n_before = c32.cnt;
     if (n_before > a.k) c32.compact(a.k, bq, rel);
     const int nsurv = c32.cnt;
-    const bool overflow = c32.overflow != 0;
+    const bool overflow = c32.overflow != 0 || nsurv > ECAP;
     TopK<ECAP> &tk = *reinterpret_cast<TopK<ECAP> *>(regA);  // aliases t2/lut: no TMA is in flight any more
     double *xs = reinterpret_cast<double *>(regA + tk_bytes) + (size_t)(tid >> 5) * M * (S + 1);
     tk.init();
@@ -476,9 +605,9 @@ __global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_fast(FastArgs a, TopkOu
             if (e < nsurv) {
                 const int ps = c32.pos[e], pb = c32.probe[e];
                 const int l = pr[pb];
-                dv = exact_adc_warp(a.C + (int64_t)l * a.d, qv, a.perm, a.P, a.codes + (int64_t)ps * M, M, ks, S, xs);
-                sq = (((unsigned long long)pb) << 32) | (unsigned long long)(ps - a.list_off[l]);
-                pay = a.iids[ps];
+                dv = exact_adc_warp(a.C + (int64_t)l * a.d, qv, a.perm, a.P, a.ocodes + (int64_t)ps * M, M, ks, S, xs);
+                sq = (((unsigned long long)pb) << 32) | (unsigned long long)a.orank[ps];
+                pay = a.oiids[ps];
             }
             tk.push(e < nsurv && lane == 0, dv, sq, pay);
         }

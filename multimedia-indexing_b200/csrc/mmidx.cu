@@ -146,6 +146,8 @@ struct mmidx_index {
     // IVFPQ CSR
     bool sealed = false;
     DevBuf csr_codes, csr_iids, dlist_off, dlist_len;
+    DevBuf csr_ocodes, csr_oiids, csr_orank;  // fast path: conflict-aware order inside each list
+    bool reorder = true;                      // MMIDX_REORDER=0 keeps insertion order (for A/B measurements)
     std::vector<int32_t> h_list_len;
     std::vector<int64_t> h_list_off;
     cudaStream_t stream = nullptr;
@@ -160,9 +162,7 @@ struct mmidx_index {
     size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
 };
 
-struct Launches {
-    int n = 0;
-};
+static bool fast_eligible(const mmidx_index *ix);
 
 static int check_device(int device) {
     int cnt = 0;
@@ -242,6 +242,7 @@ extern "C" int mmidx_create(const mmidx_params *pp, mmidx_t **out) {
     }
     if (const char *e = getenv("MMIDX_MODE")) ix->force_exact = strcmp(e, "exact") == 0;
     if (const char *e = getenv("MMIDX_STATS")) ix->want_stats = atoi(e) != 0;
+    if (const char *e = getenv("MMIDX_REORDER")) ix->reorder = atoi(e) != 0;
     if (const char *e = getenv("MMIDX_LUT_CHUNK_MB")) {
         long v = atol(e);
         if (v >= 1) ix->lut_chunk_bytes = (size_t)v << 20;
@@ -283,6 +284,12 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
     DeviceGuard g(ix->device);
     delete ix;
     return MMIDX_OK;
+}
+
+__global__ void k_identity_order(const int64_t *__restrict__ list_off, const int32_t *__restrict__ list_len,
+                                 int32_t *__restrict__ src) {
+    const int64_t start = list_off[blockIdx.x];
+    for (int i = threadIdx.x; i < list_len[blockIdx.x]; i += blockDim.x) src[start + i] = i;
 }
 
 __global__ void k_transpose(const double *__restrict__ A, int rows, int cols, double *__restrict__ At) {
@@ -619,6 +626,36 @@ static int seal(mmidx_index *ix) {
         CK(cudaStreamSynchronize(st));
     }
     CK(cudaStreamSynchronize(st));
+    if (fast_eligible(ix)) {
+        // second copy of the lists in a bank-conflict-aware order (fast_scan.cuh); offer order kept in orank
+        const int m = ix->p.m;
+        RET(ix->csr_ocodes.reserve((size_t)total * cb, 0, st));
+        RET(ix->csr_oiids.reserve((size_t)total * sizeof(int32_t), 0, st));
+        RET(ix->csr_orank.reserve((size_t)total * sizeof(int32_t), 0, st));
+        CK(cudaMemsetAsync(ix->csr_ocodes.p, 0, (size_t)total * cb, st));
+        CK(cudaMemsetAsync(ix->csr_oiids.p, 0xff, (size_t)total * sizeof(int32_t), st));
+        Scratch sc(st);
+        int32_t *src;
+        RET(sc.get(&src, (size_t)total));
+        if (ix->reorder) {
+            if (m == 8)
+                k_reorder_lists<8><<<nlist, MMIDX_NT, 0, st>>>(ix->csr_codes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
+                                                              ix->dlist_len.as<int32_t>(), src);
+            else
+                k_reorder_lists<16><<<nlist, MMIDX_NT, 0, st>>>(ix->csr_codes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
+                                                               ix->dlist_len.as<int32_t>(), src);
+            RET(post_launch("k_reorder_lists", nullptr));
+        } else {
+            k_identity_order<<<nlist, MMIDX_NT, 0, st>>>(ix->dlist_off.as<int64_t>(), ix->dlist_len.as<int32_t>(), src);
+            RET(post_launch("k_identity_order", nullptr));
+        }
+        k_apply_order<<<nlist, MMIDX_NT, 0, st>>>(ix->csr_codes.as<uint8_t>(), ix->csr_iids.as<int32_t>(),
+                                                 ix->dlist_off.as<int64_t>(), ix->dlist_len.as<int32_t>(), src, m,
+                                                 ix->csr_ocodes.as<uint8_t>(), ix->csr_oiids.as<int32_t>(),
+                                                 ix->csr_orank.as<int32_t>());
+        RET(post_launch("k_apply_order", nullptr));
+        CK(cudaStreamSynchronize(st));
+    }
     ix->sealed = true;
     return MMIDX_OK;
 }
@@ -1018,8 +1055,8 @@ static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, co
 // ---------------------------------------------------------------------------------------------------------
 static bool fast_eligible(const mmidx_index *ix) {
     if (ix->p.type != MMIDX_IVFPQ || ix->force_exact) return false;
-    if (ix->p.ks > 256 || (ix->p.m != 8 && ix->p.m != 16)) return false;
-    if (((int64_t)ix->p.m * ix->p.ks) % 4 != 0) return false;
+    // the fused kernel is specialised for byte codes with full 256-entry sub-tables and 8 or 16 sub-quantizers
+    if (ix->p.ks != 256 || (ix->p.m != 8 && ix->p.m != 16)) return false;
     return true;
 }
 
@@ -1081,6 +1118,9 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     a.probes = dprobes;
     a.codes = ix->csr_codes.as<uint8_t>();
     a.iids = ix->csr_iids.as<int32_t>();
+    a.ocodes = ix->csr_ocodes.as<uint8_t>();
+    a.oiids = ix->csr_oiids.as<int32_t>();
+    a.orank = ix->csr_orank.as<int32_t>();
     a.list_off = ix->dlist_off.as<int64_t>();
     a.list_len = ix->dlist_len.as<int32_t>();
     a.d = ix->p.d;
@@ -1123,7 +1163,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     StageMark sm3(ix, st, 3);
     {
         // items whose error band overflowed the fp32 collector (massive exact duplicates): table-free exact scan
-        constexpr int DCAP = (CAP32 <= 1024) ? 1024 : 2048;
+        constexpr int DCAP = 1024;  // k <= 256 on this path
         const size_t dsmem = topk_bytes<DCAP>();
         RET(set_smem(k_ivfpq_scan_direct<DCAP>, dsmem));
         const int dg = (int)std::min<int64_t>(nq * nsplit, 296);
@@ -1174,13 +1214,8 @@ static int ivfpq_chunk_fast_dispatch(mmidx_index *ix, const double *dQ, int64_t 
                                      cudaStream_t st, int *launches) {
 #define FASTCALL(CAPV, MV) \
     return ivfpq_chunk_fast<CAPV, MV>(ix, dQ, nq, k, w, res, res_tie, amb_list, amb_count, resolve_ties, st, launches)
-    if (ix->p.m == 8) {
-        if (k <= 256) FASTCALL(1024, 8);
-        FASTCALL(2048, 8);
-    } else {
-        if (k <= 256) FASTCALL(1024, 16);
-        FASTCALL(2048, 16);
-    }
+    if (ix->p.m == 8) FASTCALL(2048, 8);
+    FASTCALL(2048, 16);
 #undef FASTCALL
 }
 
@@ -1209,7 +1244,7 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(seal(ix));
     }
-    const bool fast = fast_eligible(ix) && k <= 512;  // larger k: exact ADC-table kernels
+    const bool fast = fast_eligible(ix) && k <= 256;  // larger k: exact ADC-table kernels
     if (fast && !ix->fast_ready) {
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(prepare_fast(ix));
