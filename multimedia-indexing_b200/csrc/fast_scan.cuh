@@ -190,6 +190,8 @@ struct FastArgs {
     const int32_t *orank;     // insertion rank (= offer order inside the list) of every reordered entry
     const int64_t *list_off;
     const int32_t *list_len;
+    const float *sall;        // [nq][w][m]  s[q][probe][j] (k_fast_prep)
+    const double *bq;         // [nq]        error radius of the fp32 distances of query q (k_fast_prep)
     int d, m, ks, S, w, k, nsplit;
     int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
     int32_t *fb_count;
@@ -213,7 +215,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 // ADC table entry of sub-quantizer J for byte I of a packed code word (ks == 256: 1 KiB per sub-table)
-#define MMIDX_LK(J, word, I) lds_f32<(J) * 1024>(lb + (__byte_perm((word), 0, 0x4440 | (I)) << 2))
+#define MMIDX_LK(J, word, I) lut[(J) * 256 + __byte_perm((word), 0, 0x4440 | (I))]
 
 // CTA-wide collector on fp32 keys with an error-band slack (see the header comment).
 template <int CAP>
@@ -222,8 +224,7 @@ struct TopK32 {
     static constexpr int KEEP_MAX = CAP / 2;
     static constexpr int PER = CAP / MMIDX_NT;
     float key[CAP];
-    int pos[CAP];
-    int probe[CAP];
+    unsigned int pk[CAP];  // (probe rank << 22) | position inside the (re-ordered) list
     unsigned int hist[256];
     float thr32;  // admission threshold: candidates with d32 > thr32 are provably outside the result
     int cnt, overflow;
@@ -239,7 +240,7 @@ struct TopK32 {
     }
 
     // all 32 lanes of a converged warp
-    __device__ __forceinline__ void push(bool pred, float d, int ps, int pb) {
+    __device__ __forceinline__ void push(bool pred, float d, unsigned int packed) {
         const unsigned mask = __ballot_sync(0xffffffffu, pred);
         if (mask == 0) return;
         const int lane = threadIdx.x & 31;
@@ -250,8 +251,7 @@ struct TopK32 {
         if (pred) {
             const int slot = base + __popc(mask & ((1u << lane) - 1u));
             key[slot] = d;
-            pos[slot] = ps;
-            probe[slot] = pb;
+            pk[slot] = packed;
         }
     }
 
@@ -315,14 +315,13 @@ struct TopK32 {
         const double U = (double)kth + rel * fabs((double)kth) + bq;
         const float keep32 = __double2float_ru((U + bq) * (1.0 + 2.0 * rel));
         float d[PER];
-        int ps[PER], pb[PER];
+        unsigned int pp[PER];
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
             const int i = tid + e * MMIDX_NT;
             if (i < n) {
                 d[e] = key[i];
-                ps[e] = pos[i];
-                pb[e] = probe[i];
+                pp[e] = pk[i];
             }
         }
         if (tid == 0) s_newcnt = 0;
@@ -334,8 +333,7 @@ struct TopK32 {
                 const int slot = atomicAdd(&s_newcnt, 1);
                 if (slot < KEEP_MAX) {
                     key[slot] = d[e];
-                    pos[slot] = ps[e];
-                    probe[slot] = pb[e];
+                    pk[slot] = pp[e];
                 }
             }
         }
@@ -382,8 +380,10 @@ __device__ __forceinline__ double exact_adc_warp(const double *__restrict__ Cl, 
                                                  double *xs) {
     const int lane = threadIdx.x & 31;
     const int d = m * S;
+    const int sh = ((S & (S - 1)) == 0) ? (31 - __clz(S)) : -1;
     for (int e = lane; e < d; e += 32) {
-        const int j = e / S, t = e - j * S;
+        const int j = (sh >= 0) ? (e >> sh) : (e / S);
+        const int t = e - j * S;
         int src = e;
         if (perm) src = perm[src];
         const double r = __dsub_rn(Cl[src], qv[src]);
@@ -406,53 +406,105 @@ struct FastExactCap {
     static constexpr int value = 512;  // exact collector for the survivors; more survivors than this -> direct kernel
 };
 
+constexpr int FAST_POS_BITS = 22;  // lists longer than 2^22 entries disable the fast path (host check)
+
+// Per-query pre-pass: s[q][p][j] = sum_t q_t (q_t - 2 C_l,t) over the (permuted) sub-vector j of probe p, in
+// binary64 then rounded to fp32, and the error radius Bq of the query (header comment).  grid nq.
+__global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict__ Q, const double *__restrict__ C,
+                                                        const int32_t *__restrict__ perm, const int32_t *__restrict__ probes,
+                                                        const float *__restrict__ t1max, const float *__restrict__ pmax,
+                                                        int d, int m, int S, int w, float *__restrict__ sall,
+                                                        double *__restrict__ bq) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *qv = reinterpret_cast<double *>(smem_raw);  // [d]
+    double *qn = qv + d;                                // [m]
+    float *bterm = reinterpret_cast<float *>(qn + m);   // [m]
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    for (int i = tid; i < d; i += MMIDX_NT) qv[i] = Q[q * (int64_t)d + i];
+    if (tid < m) bterm[tid] = 0.f;
+    __syncthreads();
+    if (tid < m) {
+        double n2 = 0.0;
+        for (int t = 0; t < S; ++t) {
+            int src = tid * S + t;
+            if (perm) src = perm[src];
+            n2 += qv[src] * qv[src];
+        }
+        qn[tid] = sqrt(n2) * (1.0 + 1e-12);
+    }
+    __syncthreads();
+    const int32_t *pr = probes + q * w;
+    for (int e = tid; e < w * m; e += MMIDX_NT) {
+        const int p = e / m, j = e - p * m;
+        const int l = pr[p];
+        const double *Cl = C + (int64_t)l * d;
+        double acc = 0.0;
+        for (int t = 0; t < S; ++t) {
+            int src = j * S + t;
+            if (perm) src = perm[src];
+            const double qt = qv[src];
+            acc += qt * (qt - 2.0 * Cl[src]);
+        }
+        sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
+        const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + (4.0 * S + 14.0) * qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
+        atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double b = 0.0;
+        for (int j = 0; j < m; ++j) b += (double)bterm[j];
+        bq[q] = 1.02 * 5.9604644775390625e-08 * b;
+    }
+}
+
 // grid (nsplit, nq).  CTA (s, q) handles probes s, s+nsplit, ... of query q in rank order.
+// Shared memory: TopK32 | t2 | stage (TMA target: T1 row of the next probe) | lut[2] | qv.  The only block-wide
+// barriers in the probe loop are the collector's round barriers: the table of probe p+1 is built into the
+// other lut buffer, and `stage` is refilled right after the first round barrier of each probe.
 template <int CAP32, int M>
 __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
     constexpr int ECAP = FastExactCap<CAP32>::value;
+    constexpr int ks = 256;  // the fused kernel is specialised for full byte codes (host checks ks == 256)
+    constexpr int nent = M * ks;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TopK32<CAP32> &c32 = *reinterpret_cast<TopK32<CAP32> *>(smem_raw);
     const size_t c32_bytes = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
-    const int nent = M * a.ks;
-    // region A (scan phase): t2 | lut0 | lut1.   Aliased in the final phase by: TopK<ECAP> | per-warp xs
+    // region A (scan phase): t2 | stage | lut0 | lut1.   Aliased in the final phase by: TopK<ECAP> | per-warp xs
     unsigned char *regA = smem_raw + c32_bytes;
     float *t2 = reinterpret_cast<float *>(regA);   // [nent]
-    float *lut0 = t2 + nent;                       // [nent]  (TMA target, then LUT in place)
+    float *stage = t2 + nent;                      // [nent]
+    float *lut0 = stage + nent;                    // [nent]
     float *lut1 = lut0 + nent;                     // [nent]
     const size_t tk_bytes = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
     const size_t xs_bytes = (size_t)(MMIDX_NT / 32) * M * (a.S + 1) * sizeof(double);
-    const size_t regA_bytes = max((size_t)3 * nent * sizeof(float), tk_bytes + xs_bytes);
+    const size_t regA_bytes = max((size_t)4 * nent * sizeof(float), tk_bytes + xs_bytes);
     double *qv = reinterpret_cast<double *>(regA + ((regA_bytes + 15) & ~(size_t)15));  // [d] raw query
-    double *qn = qv + a.d;                                                             // [M] ||q_j||
-    double *sj = qn + M;                                                               // [M] s of the current probe
-    float *bterm = reinterpret_cast<float *>(sj + M);                                  // [M] max_p error term
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bterm + M + (M & 1));                // [2]
-    double *s_bq = reinterpret_cast<double *>(bars + 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(qv + a.d);                            // [1]
 
     const int tid = threadIdx.x;
     const int s = blockIdx.x;
     const int64_t q = blockIdx.y;
     const int32_t *pr = a.probes + q * a.w;
     const uint32_t t1_bytes = (uint32_t)(nent * sizeof(float));
-    const int S = a.S, ks = a.ks;
+    const int S = a.S;
     const double rel = (double)M * 5.9604644775390625e-08;
+    const double bq = a.bq[q];
 
     c32.init();
     if (tid == 0) {
         mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
-    if (tid < M) bterm[tid] = 0.f;
     for (int i = tid; i < a.d; i += MMIDX_NT) qv[i] = a.Q[q * (int64_t)a.d + i];
     __syncthreads();
     if (tid == 0 && s < a.w) {
         mbar_arrive_expect_tx(&bars[0], t1_bytes);
-        tma_load_1d(lut0, a.T1 + (int64_t)pr[s] * nent, t1_bytes, &bars[0]);
+        tma_load_1d(stage, a.T1 + (int64_t)pr[s] * nent, t1_bytes, &bars[0]);
     }
-    // ---- per-query prologue: T2[j][c] = 2 * sum_t q32[perm(jS+t)] * P32t[j][t][c];  ||q_j||;  error radius Bq ----
+    // ---- per-query prologue: T2[j][c] = 2 * sum_t q32[perm(jS+t)] * P32t[j][t][c] ----
     for (int e = tid; e < nent; e += MMIDX_NT) {
-        const int j = e / ks, c = e - j * ks;
+        const int j = e >> 8, c = e & 255;
         const float *pp = a.P32t + (int64_t)j * S * ks + c;
         float acc = 0.f;
         for (int t = 0; t < S; ++t) {
@@ -462,85 +514,54 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
         }
         t2[e] = 2.f * acc;
     }
-    if (tid < M) {
-        double n2 = 0.0;
-        for (int t = 0; t < S; ++t) {
-            int src = tid * S + t;
-            if (a.perm) src = a.perm[src];
-            n2 += qv[src] * qv[src];
-        }
-        qn[tid] = sqrt(n2) * (1.0 + 1e-12);
-    }
-    __syncthreads();
-    for (int e = tid; e < a.w * M; e += MMIDX_NT) {  // (probe, j) pairs of this query (all splits: same Bq)
-        const int p = e / M, j = e - p * M;
-        const int l = pr[p];
-        const double *Cl = a.C + (int64_t)l * a.d;
-        double acc = 0.0;
-        for (int t = 0; t < S; ++t) {
-            int src = j * S + t;
-            if (a.perm) src = a.perm[src];
-            const double qt = qv[src];
-            acc += qt * (qt - 2.0 * Cl[src]);
-        }
-        const double term = 3.0 * (double)a.t1max[(int64_t)l * M + j] + (4.0 * S + 14.0) * qn[j] * (double)a.pmax[j] +
-                            2.0 * fabs(acc);
-        atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double b = 0.0;
-        for (int j = 0; j < M; ++j) b += (double)bterm[j];
-        *s_bq = 1.02 * 5.9604644775390625e-08 * b;
-    }
-    __syncthreads();
-    const double bq = *s_bq;
+    // (t2 is published by the first round barrier below; each thread only re-reads the entries it wrote
+    //  in the table build, which uses the same e = tid + 256*i mapping)
 
     unsigned long long n_cand = 0;
     int it = 0;
     for (int p = s; p < a.w; p += a.nsplit, ++it) {
-        const int cur = it & 1;
-        float *lut = cur ? lut1 : lut0;
+        float *lut = (it & 1) ? lut1 : lut0;
         const int l = pr[p];
-        if (tid == 0 && p + a.nsplit < a.w) {
-            // the other buffer was last read in iteration it-1, which ended with a barrier
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&bars[cur ^ 1], t1_bytes);
-            tma_load_1d(cur ? lut0 : lut1, a.T1 + (int64_t)pr[p + a.nsplit] * nent, t1_bytes, &bars[cur ^ 1]);
-        }
         const int64_t start = a.list_off[l];
         const int len = a.list_len[l];  // 0 for lists another shard owns: nothing to build or scan
-        // s[j] = sum_t q_t (q_t - 2 C_l,t) over the (permuted) sub-vector j, binary64
-        if (tid < M && len > 0) {
-            const double *Cl = a.C + (int64_t)l * a.d;
-            double acc = 0.0;
-            for (int t = 0; t < S; ++t) {
-                int src = tid * S + t;
-                if (a.perm) src = a.perm[src];
-                const double qt = qv[src];
-                acc += qt * (qt - 2.0 * Cl[src]);
-            }
-            sj[tid] = acc;
-        }
-        __syncthreads();
-        mbar_wait(&bars[cur], (uint32_t)((it >> 1) & 1));
-        // LUT in place: lut = T1[l] + T2 + s
-        if (len > 0)
-            for (int e = tid; e < nent; e += MMIDX_NT) lut[e] = (lut[e] + t2[e]) + __double2float_rn(sj[e / ks]);
-        const uint8_t *lc = a.ocodes + start * M;
-        const uint32_t lb = smem_u32(lut);
-        constexpr int ROUND = TopK32<CAP32>::ROUND;
-        for (int base = 0; base < len; base += ROUND) {
-            c32.maybe_compact(a.k, bq, rel);  // contains the round barrier (also publishes the LUT on round 0)
-            const float thr32 = c32.thr32;
-            constexpr int CPT = (M == 8) ? 2 : 1;  // candidates per 128-bit load
+        mbar_wait(&bars[0], (uint32_t)(it & 1));
+        // ADC table of this probe: lut = T1[l] + T2 + s   (thread tid owns entries tid + 256*j, i.e. one per j)
+        if (len > 0) {
+            const float *sp = a.sall + (q * (int64_t)a.w + p) * M;
 #pragma unroll
-            for (int e = 0; e < ROUND / (MMIDX_NT * CPT); ++e) {
+            for (int j = 0; j < M; ++j) {
+                const int e = tid + 256 * j;
+                lut[e] = (stage[e] + t2[e]) + sp[j];
+            }
+        }
+        const uint8_t *lc = a.ocodes + start * M;
+        const unsigned int ptag = ((unsigned int)p) << FAST_POS_BITS;
+        constexpr int ROUND = TopK32<CAP32>::ROUND;
+        constexpr int CPT = (M == 8) ? 2 : 1;              // candidates per 128-bit load
+        constexpr int NE = ROUND / (MMIDX_NT * CPT);       // loads per thread per round
+        for (int base = 0; base < len || base == 0; base += ROUND) {
+            c32.maybe_compact(a.k, bq, rel);  // round barrier: publishes the table, ends the previous probe's reads
+            if (base == 0 && tid == 0 && p + a.nsplit < a.w) {
+                // every thread has consumed `stage`: the next probe's T1 row lands while this list is scanned
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&bars[0], t1_bytes);
+                tma_load_1d(stage, a.T1 + (int64_t)pr[p + a.nsplit] * nent, t1_bytes, &bars[0]);
+            }
+            if (base >= len) break;
+            const float thr32 = c32.thr32;
+            uint4 cw[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {  // all loads of the round in flight before the first lookup
+                const int i0 = base + (e * MMIDX_NT + tid) * CPT;
+                cw[e] = make_uint4(0, 0, 0, 0);
+                if (i0 < len) cw[e] = ld_nc_u4(lc + (int64_t)i0 * M);
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
                 // warp-uniform skip of the list tail (push() only synchronises within the warp)
                 if (base + (e * MMIDX_NT + (tid & ~31)) * CPT >= len) continue;
                 const int i0 = base + (e * MMIDX_NT + tid) * CPT;
-                uint4 c = make_uint4(0, 0, 0, 0);
-                if (i0 < len) c = ld_nc_u4(lc + (int64_t)i0 * M);
+                const uint4 c = cw[e];
                 if (M == 8) {
                     float d0 = MMIDX_LK(0, c.x, 0);
                     float d1 = MMIDX_LK(0, c.z, 0);
@@ -558,8 +579,8 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
                     d1 += MMIDX_LK(6, c.w, 2);
                     d0 += MMIDX_LK(7, c.y, 3);
                     d1 += MMIDX_LK(7, c.w, 3);
-                    c32.push((i0 < len) && d0 <= thr32, d0, (int)(start + i0), p);
-                    c32.push((i0 + 1 < len) && d1 <= thr32, d1, (int)(start + i0 + 1), p);
+                    c32.push((i0 < len) && d0 <= thr32, d0, ptag | (unsigned int)i0);
+                    c32.push((i0 + 1 < len) && d1 <= thr32, d1, ptag | (unsigned int)(i0 + 1));
                 } else {
                     float d0 = MMIDX_LK(0, c.x, 0);
                     float d1 = MMIDX_LK(1, c.x, 1);
@@ -578,12 +599,11 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
                     d0 += MMIDX_LK(14, c.w, 2);
                     d1 += MMIDX_LK(15, c.w, 3);
                     d0 += d1;
-                    c32.push((i0 < len) && d0 <= thr32, d0, (int)(start + i0), p);
+                    c32.push((i0 < len) && d0 <= thr32, d0, ptag | (unsigned int)i0);
                 }
             }
         }
         n_cand += (unsigned long long)len;
-        __syncthreads();  // all reads of `lut` done before it is refilled two iterations later
     }
 
     // ---- final phase: shrink to the error band, evaluate the survivors exactly, exact top-k ----
@@ -592,7 +612,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     if (n_before > a.k) c32.compact(a.k, bq, rel);
     const int nsurv = c32.cnt;
     const bool overflow = c32.overflow != 0 || nsurv > ECAP;
-    TopK<ECAP> &tk = *reinterpret_cast<TopK<ECAP> *>(regA);  // aliases t2/lut: no TMA is in flight any more
+    TopK<ECAP> &tk = *reinterpret_cast<TopK<ECAP> *>(regA);  // aliases t2/stage/lut: no TMA is in flight any more
     double *xs = reinterpret_cast<double *>(regA + tk_bytes) + (size_t)(tid >> 5) * M * (S + 1);
     tk.init();
     if (!overflow) {
@@ -603,9 +623,11 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
             unsigned long long sq = 0ull;
             int pay = 0;
             if (e < nsurv) {
-                const int ps = c32.pos[e], pb = c32.probe[e];
+                const unsigned int packed = c32.pk[e];
+                const int pb = (int)(packed >> FAST_POS_BITS);
                 const int l = pr[pb];
-                dv = exact_adc_warp(a.C + (int64_t)l * a.d, qv, a.perm, a.P, a.ocodes + (int64_t)ps * M, M, ks, S, xs);
+                const int64_t ps = a.list_off[l] + (int64_t)(packed & ((1u << FAST_POS_BITS) - 1u));
+                dv = exact_adc_warp(a.C + (int64_t)l * a.d, qv, a.perm, a.P, a.ocodes + ps * M, M, ks, S, xs);
                 sq = (((unsigned long long)pb) << 32) | (unsigned long long)a.orank[ps];
                 pay = a.oiids[ps];
             }

@@ -157,6 +157,7 @@ struct mmidx_index {
     // fast path tables (fast_scan.cuh), rebuilt when a quantizer or the permutation changes
     DevBuf dT1, dP32t, dt1max, dpmax, dstats;
     bool fast_ready = false;
+    bool fast_len_ok = true;   // every list shorter than 2^22 entries (packed payload of the fp32 collector)
     bool force_exact = false;  // MMIDX_MODE=exact
     bool want_stats = false;   // MMIDX_STATS=1
     size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
@@ -597,7 +598,9 @@ static int seal(mmidx_index *ix) {
     std::fill(ix->h_list_len.begin(), ix->h_list_len.end(), 0);
     for (int64_t i = 0; i < nl; ++i) ix->h_list_len[ix->h_list[i]]++;
     int64_t pos = 0;
+    ix->fast_len_ok = true;
     for (int l = 0; l < nlist; ++l) {
+        if (ix->h_list_len[l] >= (1 << FAST_POS_BITS)) ix->fast_len_ok = false;
         ix->h_list_off[l] = pos;
         pos += (ix->h_list_len[l] + 15) & ~15;  // 16-entry aligned starts: 128-bit loads for any code width
     }
@@ -1089,9 +1092,9 @@ static size_t fast_smem_bytes(int ks, int S, int d) {
     const size_t c32b = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
     const size_t tkb = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
     const size_t xsb = (size_t)(MMIDX_NT / 32) * M * (S + 1) * sizeof(double);
-    size_t regA = std::max((size_t)3 * M * ks * sizeof(float), tkb + xsb);
+    size_t regA = std::max((size_t)4 * M * ks * sizeof(float), tkb + xsb);
     regA = (regA + 15) & ~(size_t)15;
-    return c32b + regA + (size_t)d * 8 + 2 * (size_t)M * 8 + ((size_t)M + (M & 1)) * 4 + 16 + 8 + 64;
+    return c32b + regA + (size_t)d * 8 + 16 + 64;
 }
 
 template <int CAP32, int M>
@@ -1131,6 +1134,19 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     a.k = k;
     a.nsplit = nsplit;
     a.stats = ix->want_stats ? ix->dstats.as<unsigned long long>() : nullptr;
+    {
+        // per-(query, probe) terms of the table decomposition and the per-query error radius
+        float *sall;
+        double *bq;
+        RET(sc.get(&sall, (size_t)nq * w * M));
+        RET(sc.get(&bq, (size_t)nq));
+        StageMark sm(ix, st, 1);
+        const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)M * 4 + 16;
+        k_fast_prep<<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.d, M, a.S, w, sall, bq);
+        RET(post_launch("k_fast_prep", launches));
+        a.sall = sall;
+        a.bq = bq;
+    }
     RET(sc.get(&a.fb_list, (size_t)nq * nsplit));
     RET(sc.get(&a.fb_count, 1));
     CK(cudaMemsetAsync(a.fb_count, 0, sizeof(int32_t), st));
@@ -1244,7 +1260,7 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(seal(ix));
     }
-    const bool fast = fast_eligible(ix) && k <= 256;  // larger k: exact ADC-table kernels
+    const bool fast = fast_eligible(ix) && ix->fast_len_ok && k <= 256;  // otherwise: exact ADC-table kernels
     if (fast && !ix->fast_ready) {
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(prepare_fast(ix));
