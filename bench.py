@@ -355,10 +355,11 @@ def run_gpu(args, rank, world, local_rank):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))["dram_bytes_per_step"]
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "k_ivfpq_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "k_ivfpq_scan_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_step": scan_bytes, "kernel_ms_per_step": scan_ms,
-            "note": "codes (12 MB) are L2-resident after first touch; fp64 ADC tables make this kernel shared-memory/LUT-build bound, not HBM bound"}
+            "note": "algorithmic bytes = sum over probed lists of len*(m+4); the 12 MB code database is L2-resident "
+                    "after first touch, the kernel is bound by shared-memory gathers + issue, see DESIGN.md 6"}
 
     # ---- CPU baseline: the oracle on a bounded query sample, all host cores ----
     cpu = None
@@ -387,7 +388,7 @@ def run_gpu(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "nq_per_step": NQ, "k": TOPK, "l2": "flushed between timed steps (256 MiB write)",
                    "sharding": "none" if world == 1 else f"IVF lists l % {world} == rank, NCCL all-gather of per-shard top-k"},
         "recall_at_100": rec,
-        "stage_ms_per_step": {"coarse": stage_ms[0] / args.steps, "lut": stage_ms[1] / args.steps,
+        "stage_ms_per_step": {"coarse": stage_ms[0] / args.steps, "prep": stage_ms[1] / args.steps,
                               "scan": stage_ms[2] / args.steps, "merge_ties": stage_ms[3] / args.steps,
                               "whole_call": stage_ms[4] / args.steps},
         "roofline": roof, "cpu_baseline": cpu,

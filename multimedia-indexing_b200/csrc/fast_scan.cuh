@@ -193,6 +193,7 @@ struct FastArgs {
     const float *sall;        // [nq][w][m]  s[q][probe][j] (k_fast_prep)
     const double *bq;         // [nq]        error radius of the fp32 distances of query q (k_fast_prep)
     int d, m, ks, S, w, k, nsplit;
+    int resolve_ties;           // 1: replay the queue's tie rule inside the kernel (unsharded, nsplit == 1)
     int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
     int32_t *fb_count;
     unsigned long long *stats;  // optional [4]: candidates, collector pushes, exact evaluations, overflows
@@ -264,9 +265,16 @@ struct TopK32 {
             const int shift = 24 - 8 * pass;
             hist[tid] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += MMIDX_NT) {
-                const unsigned kk = f32_key(key[i]);
-                if (pass == 0 || (kk >> (shift + 8)) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+            for (int i0 = 0; i0 < n; i0 += MMIDX_NT) {
+                const int i = i0 + tid;
+                bool act = i < n;
+                unsigned bin = 0;
+                if (act) {
+                    const unsigned kk = f32_key(key[i]);
+                    act = (pass == 0 || (kk >> (shift + 8)) == prefix);
+                    bin = (kk >> shift) & 255u;
+                }
+                hist_add(hist, act, bin);
             }
             __syncthreads();
             if (tid < 32) {
@@ -435,20 +443,44 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
     }
     __syncthreads();
     const int32_t *pr = probes + q * w;
-    for (int e = tid; e < w * m; e += MMIDX_NT) {
-        const int p = e / m, j = e - p * m;
-        const int l = pr[p];
-        const double *Cl = C + (int64_t)l * d;
-        double acc = 0.0;
-        for (int t = 0; t < S; ++t) {
+    if ((S & (S - 1)) == 0 && S <= 32) {
+        // S consecutive lanes share one (probe, j) pair: the C sub-vector is read as one contiguous segment
+        // (any summation order is fine here: s only feeds the fp32 table and its error term)
+        const int lane = tid & 31, warp = tid >> 5;
+        const int per_warp = 32 / S;
+        const int sub = lane / S, t = lane - sub * S;
+        for (int e0 = warp * per_warp; e0 < w * m; e0 += (MMIDX_NT / 32) * per_warp) {
+            const int e = e0 + sub;
+            const bool valid = e < w * m;
+            const int p = valid ? e / m : 0, j = valid ? e - p * m : 0;
+            const int l = pr[p];
             int src = j * S + t;
             if (perm) src = perm[src];
             const double qt = qv[src];
-            acc += qt * (qt - 2.0 * Cl[src]);
+            double acc = valid ? qt * (qt - 2.0 * C[(int64_t)l * d + src]) : 0.0;
+            for (int o = S >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (valid && t == 0) {
+                sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
+                const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + (4.0 * S + 14.0) * qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
+                atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
+            }
         }
-        sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
-        const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + (4.0 * S + 14.0) * qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
-        atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
+    } else {
+        for (int e = tid; e < w * m; e += MMIDX_NT) {
+            const int p = e / m, j = e - p * m;
+            const int l = pr[p];
+            const double *Cl = C + (int64_t)l * d;
+            double acc = 0.0;
+            for (int t = 0; t < S; ++t) {
+                int src = j * S + t;
+                if (perm) src = perm[src];
+                const double qt = qv[src];
+                acc += qt * (qt - 2.0 * Cl[src]);
+            }
+            sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
+            const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + (4.0 * S + 14.0) * qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
+            atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -632,6 +664,44 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
                 pay = a.oiids[ps];
             }
             tk.push(e < nsurv && lane == 0, dv, sq, pay);
+        }
+    }
+    // Exact ties cut at the k-th boundary: without overflow the survivors contain EVERY candidate with an exact
+    // distance <= T (a candidate outside the band is strictly farther than T), so the queue's rule
+    // (tie_resolve.cuh) can be replayed here on the survivors alone: among the first k entries with dist <= T in
+    // offer order, the latest-offered tied entries survive.  Losers get dist = +inf and drop out in finalize().
+    if (!overflow && a.resolve_ties && nsurv > a.k) {
+        __syncthreads();
+        unsigned long long kth;
+        int need, neq;
+        tk.select_kth(nsurv, a.k, kth, need, neq);
+        if (neq > need) {  // block-uniform
+            const double T = __longlong_as_double((long long)kth);
+            int *flag = reinterpret_cast<int *>(c32.key);  // the fp32 collector is dead: reuse as scratch [nsurv]
+            // rank among the le-entries by offer sequence; A = the first k of them
+            for (int i = tid; i < nsurv; i += MMIDX_NT) {
+                int f = 0;
+                if (tk.dist[i] <= T) {
+                    int rank = 0;
+                    const unsigned long long si = tk.seq[i];
+                    for (int j = 0; j < nsurv; ++j) rank += (tk.dist[j] <= T && tk.seq[j] < si) ? 1 : 0;
+                    f = (rank < a.k) ? ((tk.dist[i] == T) ? 2 : 1) : 3;  // 2: tied entry inside A, 3: offered after t*
+                }
+                flag[i] = f;
+            }
+            __syncthreads();
+            for (int i = tid; i < nsurv; i += MMIDX_NT) {
+                const int f = flag[i];
+                bool kill = (f == 3 && tk.dist[i] == T);
+                if (f == 2) {
+                    int later = 0;  // tied entries of A offered after this one
+                    const unsigned long long si = tk.seq[i];
+                    for (int j = 0; j < nsurv; ++j) later += (flag[j] == 2 && tk.seq[j] > si) ? 1 : 0;
+                    kill = later >= need;  // only the `need` latest-offered tied entries stay
+                }
+                if (kill) tk.dist[i] = __longlong_as_double(0x7ff0000000000000LL);
+            }
+            __syncthreads();
         }
     }
     if (a.stats && tid == 0) {

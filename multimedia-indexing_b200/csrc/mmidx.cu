@@ -1133,6 +1133,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     a.w = w;
     a.k = k;
     a.nsplit = nsplit;
+    a.resolve_ties = (resolve_ties && nsplit == 1) ? 1 : 0;
     a.stats = ix->want_stats ? ix->dstats.as<unsigned long long>() : nullptr;
     {
         // per-(query, probe) terms of the table decomposition and the per-query error radius

@@ -15,6 +15,15 @@
 
 namespace mmidx {
 
+// histogram increment with warp aggregation: lanes that hit the same bin issue ONE shared-memory atomic
+// (the high-order bytes of similar distances all fall into one or two bins, which would serialise 32-way).
+// Must be called by all 32 lanes of a converged warp.
+__device__ __forceinline__ void hist_add(unsigned int *hist, bool act, unsigned bin) {
+    const unsigned key = act ? bin : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (act && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+}
+
 template <int CAP>
 struct TopK {
     static constexpr int ROUND = CAP / 2;     // max pushes between two maybe_compact() calls
@@ -70,9 +79,16 @@ struct TopK {
             const int shift = 56 - 8 * pass;
             hist[tid] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += MMIDX_NT) {
-                unsigned long long key = (unsigned long long)__double_as_longlong(dist[i]);
-                if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+            for (int i0 = 0; i0 < n; i0 += MMIDX_NT) {
+                const int i = i0 + tid;
+                bool act = i < n;
+                unsigned bin = 0;
+                if (act) {
+                    unsigned long long key = (unsigned long long)__double_as_longlong(dist[i]);
+                    act = (pass == 0 || (key >> (shift + 8)) == prefix);
+                    bin = (unsigned)(key >> shift) & 255u;
+                }
+                hist_add(hist, act, bin);
             }
             __syncthreads();
             if (tid < 32) {
