@@ -194,8 +194,16 @@ def run_gpu(args, rank, world, local_rank):
     # ---- build the index (untimed): GPU coarse-assign + residual + PQ encode of the whole database ----
     t0 = time.time()
     if world > 1:
-        from multimedia_indexing_b200.sharded import ShardedIVFPQ
-        sh = ShardedIVFPQ(D, N_DB, M_SUB, KS, M.TransformationType.None_, NLIST)
+        from multimedia_indexing_b200.sharded import HybridIVFPQ
+        # G = S list shards x R query groups (sharded.py).  Rule: shard the lists until one shard's codes + iids fit
+        # half of the 126 MB L2 (a scan that stays L2-resident), replicate beyond that.  This 12 MB index gives S = 1;
+        # BASELINE configs[3] (10M x 16 B + iids = 200 MB) gives S = 4.  MMIDX_LIST_SHARDS overrides.
+        index_bytes = N_DB * (M_SUB + 4)
+        S_auto = 1
+        while index_bytes / S_auto > 64e6 and S_auto < world:
+            S_auto *= 2
+        sh = HybridIVFPQ(D, N_DB, M_SUB, KS, M.TransformationType.None_, NLIST,
+                         int(os.environ.get("MMIDX_LIST_SHARDS", str(S_auto))))
         ix = sh.index
     else:
         sh = None
@@ -203,7 +211,7 @@ def run_gpu(args, rank, world, local_rank):
     ix.loadCoarseQuantizer(Cq)
     ix.loadProductQuantizer(P)
     ix.setW(W_PROBE)
-    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    lists, codes = sh.indexAll(X) if sh is not None else ix.indexVectors(None, X, return_codes=True)
     log(f"[bench] rank {rank}: indexed {ix.getLoadCounter()} vectors in {time.time() - t0:.1f}s")
     parity = {}
     foc = prefix + "_oracle_codes.npz"
@@ -252,7 +260,7 @@ def run_gpu(args, rank, world, local_rank):
     for _ in range(nwarm):
         step_dev()
     torch.cuda.synchronize()
-    launches_per_step = ix.lastLaunches() + (3 if sh is not None else 0)
+    launches_per_step = ix.lastLaunches() + (2 if sh is not None and sh.S > 1 else 0)  # + the device merge kernels
     ix.enableTimings(True)
     stage_ms = np.zeros(5)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -282,6 +290,8 @@ def run_gpu(args, rank, world, local_rank):
     r_iids = res[0].cpu().numpy()
     r_dist = res[1].cpu().numpy()
 
+    if sh is not None and sh.sharded is not None and os.environ.get("MMIDX_SHARD_TIMING"):
+        log(f"[bench] rank {rank} phases ms: " + json.dumps({k: round(v, 3) for k, v in sh.sharded.last_phase_ms.items()}))
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "value": qps, "ms_per_step": ms_per_step,
@@ -338,8 +348,9 @@ def run_gpu(args, rank, world, local_rank):
     rec = recall_at_k(r_iids[:N_GT], gt)
     # ---- roofline of the ADC scan kernel: algorithmic bytes = sum over probed lists of len*(m + 4) ----
     scan_bytes = ix.scanBytes(Q) if sh is None else None
-    if sh is not None:  # this rank's share of the probed lists
-        probes = ix.computeNearestCoarseIndices(Q)
+    if sh is not None:  # this rank's share: its query group's slice, the probed lists it stores
+        q0, q1, _ = sh.slice_of(NQ)
+        probes = ix.computeNearestCoarseIndices(Q[q0:q1])
         ls = ix.listSizes()
         scan_bytes = int(ls[probes].sum()) * (M_SUB + 4)
     peaks = {}
@@ -386,7 +397,9 @@ def run_gpu(args, rank, world, local_rank):
         "warmup": nwarm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "nq_per_step": NQ, "k": TOPK, "l2": "flushed between timed steps (256 MiB write)",
-                   "sharding": "none" if world == 1 else f"IVF lists l % {world} == rank, NCCL all-gather of per-shard top-k"},
+                   "sharding": "none" if world == 1 else
+                   f"{sh.S} list shards (balanced list->shard map, per-shard top-k exchanged over NCCL, device merge) x "
+                   f"{sh.R} query groups"},
         "recall_at_100": rec,
         "stage_ms_per_step": {"coarse": stage_ms[0] / args.steps, "prep": stage_ms[1] / args.steps,
                               "scan": stage_ms[2] / args.steps, "merge_ties": stage_ms[3] / args.steps,

@@ -70,6 +70,9 @@ int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C);
 /* TransformationType.RandomPermutation (PQ.java:237-241,294-298; IVFPQ.java:319-323,420-424):
  * perm[d] as produced by RandomPermutation.java:29-40; permuted[i] = v[perm[i]].  NULL clears it. */
 int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm);
+/* multi-GPU: owner[nlist] = shard that stores each inverted list (default l % shard_count); every rank must be
+ * given the same map, before the first vector is indexed.  NULL restores the default. */
+int mmidx_set_shard_map(mmidx_t *ix, const int32_t *owner);
 /* IVFPQ.setW IVFPQ.java:95-97 */
 int mmidx_set_w(mmidx_t *ix, int32_t w);
 
@@ -98,6 +101,8 @@ int mmidx_search_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, int32
                      int32_t *d_count, void *stream);
 /* ---- multi-GPU (one process per GPU; the IVF lists are sharded, l % shard_count == shard_rank) ----
  * The reference keeps ONE queue for all probed lists (IVFPQ.java:409,445).  A sharded search therefore is:
+ *   0. (optional) every rank runs mmidx_coarse_probe_dev on its nq/G slice of the queries and the probe lists
+ *      are all-gathered, so the coarse stage is not repeated G times;
  *   1. mmidx_search_shard_dev on every rank: local top-k of the lists this rank owns, plus for every result the
  *      offer sequence number d_seq[nq][k] (probe rank * 2^32 + position in list) and per query d_tie[nq], the
  *      distance at which locally tied candidates were cut (-1 if none);
@@ -107,8 +112,10 @@ int mmidx_search_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, int32
  *   4. only if *d_amb_count != 0: mmidx_tie_collect_shard_dev on every rank, all-gather, mmidx_tie_finish_dev
  *      (replays the queue's tie rule exactly, see csrc/tie_resolve.cuh).
  * All device side, asynchronous on `stream` (step 4's collect host-syncs: it is the rare path). nq <= 32768. */
-int mmidx_search_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, int32_t *d_iids,
-                           double *d_dist, int64_t *d_seq, double *d_tie, int32_t *d_count, void *stream);
+int mmidx_search_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k,
+                           const int32_t *d_probes /* [nq][w] from mmidx_coarse_probe_dev, or NULL: computed here */,
+                           int32_t *d_iids, double *d_dist, int64_t *d_seq, double *d_tie, int32_t *d_count,
+                           void *stream);
 int mmidx_merge_topk_dev(int64_t nq, int32_t k, int32_t nparts, const int32_t *d_iids, const double *d_dist,
                          const int64_t *d_seq, const double *d_tie, const int32_t *d_count,
                          int32_t *d_out_iids, double *d_out_dist, int64_t *d_out_seq, int32_t *d_out_count,
@@ -123,6 +130,9 @@ int mmidx_tie_finish_dev(int64_t nq, int32_t k, int32_t nparts, const int64_t *d
 
 /* IVFPQ.computeNearestCoarseIndices IVFPQ.java:575-601: out[nq][w], ascending coarse distance */
 int mmidx_coarse_probe(mmidx_t *ix, int64_t nq, const double *Q, int32_t w, int32_t *out);
+/* same, device side and asynchronous: lets G ranks each probe nq/G queries and all-gather the probe lists
+ * (the coarse quantizer is replicated, so the result does not depend on which rank computes it) */
+int mmidx_coarse_probe_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t w, int32_t *d_out, void *stream);
 /* computeLookupADC PQ.java:387-399: out[nq][m][ks] for already-transformed (residual) vectors V[nq][d] */
 int mmidx_pq_lut(mmidx_t *ix, int64_t nq, const double *V, double *out);
 

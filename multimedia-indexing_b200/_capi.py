@@ -50,12 +50,14 @@ _SIGS = {
     "mmidx_set_coarse_quantizer": [_vp, _vp],
     "mmidx_set_permutation": [_vp, _vp],
     "mmidx_set_w": [_vp, _i32],
+    "mmidx_set_shard_map": [_vp, _vp],
     "mmidx_add": [_vp, _i64, _vp, _vp, _vp],
     "mmidx_add_codes": [_vp, _i64, _vp, _vp],
     "mmidx_encode": [_vp, _i64, _vp, _vp, _vp],
     "mmidx_search": [_vp, _i64, _vp, _i32, _vp, _vp, _vp],
     "mmidx_search_dev": [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
-    "mmidx_search_shard_dev": [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mmidx_search_shard_dev": [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mmidx_coarse_probe_dev": [_vp, _i64, _vp, _i32, _vp, _vp],
     "mmidx_merge_topk_dev": [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mmidx_tie_collect_shard_dev": [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mmidx_tie_finish_dev": [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

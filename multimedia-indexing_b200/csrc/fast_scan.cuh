@@ -192,6 +192,9 @@ struct FastArgs {
     const int32_t *list_len;
     const float *sall;        // [nq][w][m]  s[q][probe][j] (k_fast_prep)
     const double *bq;         // [nq]        error radius of the fp32 distances of query q (k_fast_prep)
+    const float *T2;          // [nq][m*256] per-query term of the table decomposition (k_fast_t2)
+    const int32_t *oprobes;   // [nq][w]     ranks of the probes with a non-empty list on this shard, ascending
+    const int32_t *ocnt;      // [nq]
     int d, m, ks, S, w, k, nsplit;
     int resolve_ties;           // 1: replay the queue's tie rule inside the kernel (unsharded, nsplit == 1)
     int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
@@ -416,17 +419,66 @@ struct FastExactCap {
 
 constexpr int FAST_POS_BITS = 22;  // lists longer than 2^22 entries disable the fast path (host check)
 
+// T2[q][j*256 + c] = 2 * sum_t q32[perm(jS+t)] * P32t[j][t][c]: the per-query term of the table decomposition, for
+// a whole batch.  grid (ceil(nq / T2_QB), m), thread <-> c; the thread keeps its S codebook values in registers and
+// the CTA's query sub-vectors sit in shared memory (read as warp-wide broadcasts).  fp32 FMA chain, t ascending
+// (the error bound in the header assumes exactly this chain).
+constexpr int T2_QB = 32;
+
+template <int ST>
+__global__ void __launch_bounds__(MMIDX_NT) k_fast_t2(const double *__restrict__ Q, const int32_t *__restrict__ perm,
+                                                      const float *__restrict__ P32t, int64_t nq, int d, int m, int S_rt,
+                                                      float *__restrict__ T2) {
+    const int S = ST > 0 ? ST : S_rt;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *qs = reinterpret_cast<float *>(smem_raw);  // [T2_QB][S]
+    const int j = blockIdx.y, c = threadIdx.x;        // ks == 256 == blockDim.x
+    const int64_t q0 = (int64_t)blockIdx.x * T2_QB;
+    const int nb = (int)min((int64_t)T2_QB, nq - q0);
+    for (int e = threadIdx.x; e < nb * S; e += MMIDX_NT) {
+        const int qi = e / S, t = e - qi * S;
+        int src = j * S + t;
+        if (perm) src = perm[src];
+        qs[e] = __double2float_rn(Q[(q0 + qi) * (int64_t)d + src]);
+    }
+    __syncthreads();
+    const float *pp = P32t + (int64_t)j * S * 256 + c;
+    if (ST > 0) {
+        float pr[ST > 0 ? ST : 1];
+#pragma unroll
+        for (int t = 0; t < ST; ++t) pr[t] = pp[t * 256];
+        for (int qi = 0; qi < nb; ++qi) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < ST; ++t) acc = fmaf(qs[qi * ST + t], pr[t], acc);
+            T2[(q0 + qi) * (int64_t)m * 256 + j * 256 + c] = 2.f * acc;
+        }
+    } else {
+        for (int qi = 0; qi < nb; ++qi) {
+            float acc = 0.f;
+            for (int t = 0; t < S; ++t) acc = fmaf(qs[qi * S + t], pp[(int64_t)t * 256], acc);
+            T2[(q0 + qi) * (int64_t)m * 256 + j * 256 + c] = 2.f * acc;
+        }
+    }
+}
+
 // Per-query pre-pass: s[q][p][j] = sum_t q_t (q_t - 2 C_l,t) over the (permuted) sub-vector j of probe p, in
 // binary64 then rounded to fp32, and the error radius Bq of the query (header comment).  grid nq.
+// MT/ST > 0: compile-time m and S (S a power of two <= 32: S consecutive lanes share one (probe, j) pair and read
+// the centroid sub-vector as one contiguous segment); 0: generic.
+template <int MT, int ST>
 __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict__ Q, const double *__restrict__ C,
                                                         const int32_t *__restrict__ perm, const int32_t *__restrict__ probes,
                                                         const float *__restrict__ t1max, const float *__restrict__ pmax,
-                                                        int d, int m, int S, int w, float *__restrict__ sall,
-                                                        double *__restrict__ bq) {
+                                                        const int32_t *__restrict__ list_len, int d, int m_rt, int S_rt,
+                                                        int w, float *__restrict__ sall, double *__restrict__ bq,
+                                                        int32_t *__restrict__ oprobes, int32_t *__restrict__ ocnt) {
+    const int m = MT > 0 ? MT : m_rt;
+    const int S = ST > 0 ? ST : S_rt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *qv = reinterpret_cast<double *>(smem_raw);  // [d]
-    double *qn = qv + d;                                // [m]
-    float *bterm = reinterpret_cast<float *>(qn + m);   // [m]
+    float *qn = reinterpret_cast<float *>(qv + d);      // [m]  upper bound of ||q_j||
+    float *bterm = qn + m;                              // [m]
     const int tid = threadIdx.x;
     const int64_t q = blockIdx.x;
     for (int i = tid; i < d; i += MMIDX_NT) qv[i] = Q[q * (int64_t)d + i];
@@ -439,29 +491,43 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
             if (perm) src = perm[src];
             n2 += qv[src] * qv[src];
         }
-        qn[tid] = sqrt(n2) * (1.0 + 1e-12);
+        qn[tid] = __fsqrt_ru(__double2float_ru(n2 * (1.0 + 1e-12)));
     }
     __syncthreads();
     const int32_t *pr = probes + q * w;
-    if ((S & (S - 1)) == 0 && S <= 32) {
-        // S consecutive lanes share one (probe, j) pair: the C sub-vector is read as one contiguous segment
-        // (any summation order is fine here: s only feeds the fp32 table and its error term)
+    const double cS = 4.0 * S + 14.0;
+    // probe ranks with a non-empty list on this shard, in rank order (lists other shards own have length 0 here)
+    if (tid < 32) {
+        int base = 0;
+        for (int p0 = 0; p0 < w; p0 += 32) {
+            const int p = p0 + tid;
+            const bool own = p < w && list_len[pr[p]] > 0;
+            const unsigned mk = __ballot_sync(0xffffffffu, own);
+            if (own) oprobes[q * w + base + __popc(mk & ((1u << tid) - 1u))] = p;
+            base += __popc(mk);
+        }
+        if (tid == 0) ocnt[q] = base;
+    }
+    if (ST > 0) {
         const int lane = tid & 31, warp = tid >> 5;
-        const int per_warp = 32 / S;
-        const int sub = lane / S, t = lane - sub * S;
+        constexpr int SS = ST > 0 ? ST : 1;
+        constexpr int per_warp = 32 / SS;
+        const int sub = lane / SS, t = lane - sub * SS;
         for (int e0 = warp * per_warp; e0 < w * m; e0 += (MMIDX_NT / 32) * per_warp) {
             const int e = e0 + sub;
             const bool valid = e < w * m;
             const int p = valid ? e / m : 0, j = valid ? e - p * m : 0;
             const int l = pr[p];
+            const bool use = valid && list_len[l] > 0;
             int src = j * S + t;
             if (perm) src = perm[src];
             const double qt = qv[src];
-            double acc = valid ? qt * (qt - 2.0 * C[(int64_t)l * d + src]) : 0.0;
-            for (int o = S >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (valid && t == 0) {
+            double acc = use ? qt * (qt - 2.0 * C[(int64_t)l * d + src]) : 0.0;
+#pragma unroll
+            for (int o = SS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (use && t == 0) {
                 sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
-                const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + (4.0 * S + 14.0) * qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
+                const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + cS * (double)qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
                 atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
             }
         }
@@ -469,6 +535,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
         for (int e = tid; e < w * m; e += MMIDX_NT) {
             const int p = e / m, j = e - p * m;
             const int l = pr[p];
+            if (list_len[l] <= 0) continue;
             const double *Cl = C + (int64_t)l * d;
             double acc = 0.0;
             for (int t = 0; t < S; ++t) {
@@ -478,7 +545,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
                 acc += qt * (qt - 2.0 * Cl[src]);
             }
             sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
-            const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + (4.0 * S + 14.0) * qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
+            const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + cS * (double)qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
             atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
         }
     }
@@ -530,35 +597,32 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     }
     for (int i = tid; i < a.d; i += MMIDX_NT) qv[i] = a.Q[q * (int64_t)a.d + i];
     __syncthreads();
-    if (tid == 0 && s < a.w) {
+    const int32_t *op = a.oprobes + q * a.w;  // probe ranks this CTA's shard really has to scan
+    const int nop = a.ocnt[q];
+    if (tid == 0 && s < nop) {
         mbar_arrive_expect_tx(&bars[0], t1_bytes);
-        tma_load_1d(stage, a.T1 + (int64_t)pr[s] * nent, t1_bytes, &bars[0]);
+        tma_load_1d(stage, a.T1 + (int64_t)pr[op[s]] * nent, t1_bytes, &bars[0]);
     }
-    // ---- per-query prologue: T2[j][c] = 2 * sum_t q32[perm(jS+t)] * P32t[j][t][c] ----
-    for (int e = tid; e < nent; e += MMIDX_NT) {
-        const int j = e >> 8, c = e & 255;
-        const float *pp = a.P32t + (int64_t)j * S * ks + c;
-        float acc = 0.f;
-        for (int t = 0; t < S; ++t) {
-            int src = j * S + t;
-            if (a.perm) src = a.perm[src];
-            acc = fmaf(__double2float_rn(qv[src]), pp[(int64_t)t * ks], acc);
-        }
-        t2[e] = 2.f * acc;
+    // ---- per-query prologue: this query's T2 row (k_fast_t2) into shared memory ----
+    {
+        const float *t2g = a.T2 + q * (int64_t)nent;
+#pragma unroll
+        for (int j = 0; j < M; ++j) t2[tid + 256 * j] = t2g[tid + 256 * j];
     }
     // (t2 is published by the first round barrier below; each thread only re-reads the entries it wrote
     //  in the table build, which uses the same e = tid + 256*i mapping)
 
     unsigned long long n_cand = 0;
     int it = 0;
-    for (int p = s; p < a.w; p += a.nsplit, ++it) {
+    for (int ii = s; ii < nop; ii += a.nsplit, ++it) {
         float *lut = (it & 1) ? lut1 : lut0;
+        const int p = op[ii];
         const int l = pr[p];
         const int64_t start = a.list_off[l];
-        const int len = a.list_len[l];  // 0 for lists another shard owns: nothing to build or scan
+        const int len = a.list_len[l];  // > 0 by construction of oprobes
         mbar_wait(&bars[0], (uint32_t)(it & 1));
         // ADC table of this probe: lut = T1[l] + T2 + s   (thread tid owns entries tid + 256*j, i.e. one per j)
-        if (len > 0) {
+        {
             const float *sp = a.sall + (q * (int64_t)a.w + p) * M;
 #pragma unroll
             for (int j = 0; j < M; ++j) {
@@ -573,11 +637,11 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
         constexpr int NE = ROUND / (MMIDX_NT * CPT);       // loads per thread per round
         for (int base = 0; base < len || base == 0; base += ROUND) {
             c32.maybe_compact(a.k, bq, rel);  // round barrier: publishes the table, ends the previous probe's reads
-            if (base == 0 && tid == 0 && p + a.nsplit < a.w) {
+            if (base == 0 && tid == 0 && ii + a.nsplit < nop) {
                 // every thread has consumed `stage`: the next probe's T1 row lands while this list is scanned
                 fence_proxy_async();
                 mbar_arrive_expect_tx(&bars[0], t1_bytes);
-                tma_load_1d(stage, a.T1 + (int64_t)pr[p + a.nsplit] * nent, t1_bytes, &bars[0]);
+                tma_load_1d(stage, a.T1 + (int64_t)pr[op[ii + a.nsplit]] * nent, t1_bytes, &bars[0]);
             }
             if (base >= len) break;
             const float thr32 = c32.thr32;
@@ -731,9 +795,12 @@ __global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_direct(FastArgs a, Topk
         const int s = item - (int)q * a.nsplit;
         const int32_t *pr = a.probes + q * a.w;
         const double *qv = a.Q + q * (int64_t)a.d;
+        const int32_t *op = a.oprobes + q * a.w;  // same probe subset as the fast kernel's CTA (s, q)
+        const int nop = a.ocnt[q];
         __syncthreads();
         tk.init();
-        for (int p = s; p < a.w; p += a.nsplit) {
+        for (int ii = s; ii < nop; ii += a.nsplit) {
+            const int p = op[ii];
             const int l = pr[p];
             const int64_t start = a.list_off[l];
             const int len = a.list_len[l];

@@ -156,6 +156,7 @@ struct mmidx_index {
     int last_launches = 0;
     // fast path tables (fast_scan.cuh), rebuilt when a quantizer or the permutation changes
     DevBuf dT1, dP32t, dt1max, dpmax, dstats;
+    std::vector<int32_t> shard_map;  // optional list -> owning shard (default l % shard_count)
     bool fast_ready = false;
     bool fast_len_ok = true;   // every list shorter than 2^22 entries (packed payload of the fp32 collector)
     bool force_exact = false;  // MMIDX_MODE=exact
@@ -361,6 +362,26 @@ extern "C" int mmidx_set_w(mmidx_t *ix, int32_t w) {
     return MMIDX_OK;
 }
 
+static inline bool owns_list(const mmidx_index *ix, int32_t l) {
+    if (ix->shard_count <= 1) return true;
+    return (ix->shard_map.empty() ? l % ix->shard_count : ix->shard_map[l]) == ix->shard_rank;
+}
+
+extern "C" int mmidx_set_shard_map(mmidx_t *ix, const int32_t *owner) {
+    if (!ix) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "only IVFPQ is sharded by list");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (ix->n != 0) return fail(MMIDX_ERR_STATE, "the shard map must be set before any vector is indexed");
+    if (!owner) {
+        ix->shard_map.clear();
+        return MMIDX_OK;
+    }
+    for (int l = 0; l < ix->p.nlist; ++l)
+        if (owner[l] < 0 || owner[l] >= ix->shard_count) return fail(MMIDX_ERR_INVALID, "owner[%d] = %d out of range", l, owner[l]);
+    ix->shard_map.assign(owner, owner + ix->p.nlist);
+    return MMIDX_OK;
+}
+
 extern "C" int mmidx_enable_timings(mmidx_t *ix, int32_t on) {
     if (!ix) return fail(MMIDX_ERR_INVALID, "null argument");
     ix->timer.enabled = on != 0;
@@ -495,7 +516,7 @@ static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *o
                 // keep only the lists this shard owns (l % shard_count == shard_rank), iids stay global
                 hsel.clear();
                 for (int64_t i = 0; i < nb; ++i)
-                    if (hl[i] % ix->shard_count == ix->shard_rank) {
+                    if (owns_list(ix, hl[i])) {
                         hsel.push_back(i);
                         ix->h_list.push_back(hl[i]);
                         ix->h_iid.push_back((int32_t)(ix->n + b + i));
@@ -565,7 +586,7 @@ extern "C" int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, 
         sel.reserve((size_t)n * cb / ix->shard_count + 64);
         ns = 0;
         for (int64_t i = 0; i < n; ++i)
-            if (list_ids[i] % ix->shard_count == ix->shard_rank) {
+            if (owns_list(ix, list_ids[i])) {
                 sel.insert(sel.end(), src + i * cb, src + (i + 1) * cb);
                 ix->h_list.push_back(list_ids[i]);
                 ix->h_iid.push_back((int32_t)(ix->n + i));
@@ -813,14 +834,14 @@ static int smem_limit_for_luts() { return 200 * 1024; }
 template <int CAP>
 static int ivfpq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, int w, const ResultBufs &res,
                        double *res_tie, int32_t *amb_list, int32_t *amb_count, bool resolve_ties, cudaStream_t st,
-                       int *launches) {
+                       int *launches, const int32_t *given_probes) {
     Scratch sc(st);
     const int m = ix->p.m, ks = ix->p.ks;
-    int32_t *dprobes;
+    int32_t *dprobes = const_cast<int32_t *>(given_probes);
     double *dlut;
-    RET(sc.get(&dprobes, (size_t)nq * w));
     RET(sc.get(&dlut, (size_t)nq * w * lut_stride_of(ix)));
-    {
+    if (!dprobes) {
+        RET(sc.get(&dprobes, (size_t)nq * w));
         StageMark sm(ix, st, 0);
         RET(coarse_probe_dev(ix, dQ, nq, w, dprobes, sc, st, launches));
     }
@@ -1100,11 +1121,11 @@ static size_t fast_smem_bytes(int ks, int S, int d) {
 template <int CAP32, int M>
 static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k, int w, const ResultBufs &res,
                             double *res_tie, int32_t *amb_list, int32_t *amb_count, bool resolve_ties, cudaStream_t st,
-                            int *launches) {
+                            int *launches, const int32_t *given_probes) {
     Scratch sc(st);
-    int32_t *dprobes;
-    RET(sc.get(&dprobes, (size_t)nq * w));
-    {
+    int32_t *dprobes = const_cast<int32_t *>(given_probes);
+    if (!dprobes) {
+        RET(sc.get(&dprobes, (size_t)nq * w));
         StageMark sm(ix, st, 0);
         RET(coarse_probe_dev(ix, dQ, nq, w, dprobes, sc, st, launches));
     }
@@ -1139,14 +1160,38 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         // per-(query, probe) terms of the table decomposition and the per-query error radius
         float *sall;
         double *bq;
+        int32_t *oprobes, *ocnt;
+        float *T2;
+        RET(sc.get(&T2, (size_t)nq * M * 256));
         RET(sc.get(&sall, (size_t)nq * w * M));
         RET(sc.get(&bq, (size_t)nq));
+        RET(sc.get(&oprobes, (size_t)nq * w));
+        RET(sc.get(&ocnt, (size_t)nq));
         StageMark sm(ix, st, 1);
         const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)M * 4 + 16;
-        k_fast_prep<<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.d, M, a.S, w, sall, bq);
+        if (M == 8 && a.S == 16)
+            k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_len, a.d, M, a.S, w, sall, bq, oprobes, ocnt);
+        else if (M == 16 && a.S == 8)
+            k_fast_prep<16, 8><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_len, a.d, M, a.S, w, sall, bq, oprobes, ocnt);
+        else
+            k_fast_prep<0, 0><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_len, a.d, M, a.S, w, sall, bq, oprobes, ocnt);
         RET(post_launch("k_fast_prep", launches));
+        {
+            dim3 g2((unsigned)((nq + T2_QB - 1) / T2_QB), M);
+            const size_t sm2 = (size_t)T2_QB * a.S * sizeof(float);
+            if (a.S == 16)
+                k_fast_t2<16><<<g2, MMIDX_NT, sm2, st>>>(dQ, a.perm, a.P32t, nq, a.d, M, a.S, T2);
+            else if (a.S == 8)
+                k_fast_t2<8><<<g2, MMIDX_NT, sm2, st>>>(dQ, a.perm, a.P32t, nq, a.d, M, a.S, T2);
+            else
+                k_fast_t2<0><<<g2, MMIDX_NT, sm2, st>>>(dQ, a.perm, a.P32t, nq, a.d, M, a.S, T2);
+            RET(post_launch("k_fast_t2", launches));
+        }
+        a.T2 = T2;
         a.sall = sall;
         a.bq = bq;
+        a.oprobes = oprobes;
+        a.ocnt = ocnt;
     }
     RET(sc.get(&a.fb_list, (size_t)nq * nsplit));
     RET(sc.get(&a.fb_count, 1));
@@ -1228,9 +1273,9 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
 
 static int ivfpq_chunk_fast_dispatch(mmidx_index *ix, const double *dQ, int64_t nq, int k, int w, const ResultBufs &res,
                                      double *res_tie, int32_t *amb_list, int32_t *amb_count, bool resolve_ties,
-                                     cudaStream_t st, int *launches) {
+                                     cudaStream_t st, int *launches, const int32_t *given_probes) {
 #define FASTCALL(CAPV, MV) \
-    return ivfpq_chunk_fast<CAPV, MV>(ix, dQ, nq, k, w, res, res_tie, amb_list, amb_count, resolve_ties, st, launches)
+    return ivfpq_chunk_fast<CAPV, MV>(ix, dQ, nq, k, w, res, res_tie, amb_list, amb_count, resolve_ties, st, launches, given_probes)
     if (ix->p.m == 8) FASTCALL(2048, 8);
     FASTCALL(2048, 16);
 #undef FASTCALL
@@ -1253,7 +1298,8 @@ static int validate_search(mmidx_index *ix, int64_t nq, int k, int *w_out) {
 
 // device-side search over all chunks.  d_seq/d_tie non-NULL => sharded mode (no local tie resolution).
 static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k, int32_t *d_iids, double *d_dist,
-                           unsigned long long *d_seq, double *d_tie, int32_t *d_count, cudaStream_t st, bool sharded) {
+                           unsigned long long *d_seq, double *d_tie, int32_t *d_count, cudaStream_t st, bool sharded,
+                           const int32_t *d_probes = nullptr) {
     int w = 0;
     RET(validate_search(ix, nq, k, &w));
     if (nq == 0) return MMIDX_OK;
@@ -1298,13 +1344,16 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
         const bool big = cap_for(k) == 2048;
         switch (ix->p.type) {
             case MMIDX_IVFPQ:
+            {
+                const int32_t *gp = d_probes ? d_probes + q0 * w : nullptr;
                 if (fast) {
                     r = ivfpq_chunk_fast_dispatch(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count,
-                                                  !sharded, st, &launches);
+                                                  !sharded, st, &launches, gp);
                     break;
                 }
-                r = big ? ivfpq_chunk<2048>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches)
-                        : ivfpq_chunk<1024>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches);
+                r = big ? ivfpq_chunk<2048>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches, gp)
+                        : ivfpq_chunk<1024>(ix, dq, nb, k, w, res, d_tie ? d_tie + q0 : nullptr, amb_list, amb_count, !sharded, st, &launches, gp);
+            }
                 break;
             case MMIDX_PQ:
                 r = big ? pq_chunk<2048>(ix, dq, nb, k, res, amb_list, amb_count, st, &launches)
@@ -1330,13 +1379,15 @@ extern "C" int mmidx_search_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32
     return search_dev_impl(ix, nq, dQ, k, d_iids, d_dist, nullptr, nullptr, d_count, (cudaStream_t)stream, false);
 }
 
-extern "C" int mmidx_search_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, int32_t *d_iids, double *d_dist,
-                                      int64_t *d_seq, double *d_tie, int32_t *d_count, void *stream) {
+extern "C" int mmidx_search_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, const int32_t *d_probes,
+                                      int32_t *d_iids, double *d_dist, int64_t *d_seq, double *d_tie, int32_t *d_count,
+                                      void *stream) {
     if (!ix || (nq > 0 && (!dQ || !d_iids || !d_dist || !d_seq || !d_tie || !d_count)))
         return fail(MMIDX_ERR_INVALID, "null argument");
     if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "sharded search is defined for IVFPQ");
     DeviceGuard g(ix->device);
-    return search_dev_impl(ix, nq, dQ, k, d_iids, d_dist, (unsigned long long *)d_seq, d_tie, d_count, (cudaStream_t)stream, true);
+    return search_dev_impl(ix, nq, dQ, k, d_iids, d_dist, (unsigned long long *)d_seq, d_tie, d_count, (cudaStream_t)stream, true,
+                           d_probes);
 }
 
 extern "C" int mmidx_merge_topk_dev(int64_t nq, int32_t k, int32_t nparts, const int32_t *d_iids, const double *d_dist,
@@ -1517,6 +1568,24 @@ extern "C" int mmidx_coarse_probe(mmidx_t *ix, int64_t nq, const double *Q, int3
         CK(cudaStreamSynchronize(st));
     }
     ix->last_launches = launches;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_coarse_probe_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t w, int32_t *d_out, void *stream) {
+    if (!ix || (nq > 0 && (!dQ || !d_out))) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "coarse probe applies to IVFPQ only");
+    if (!ix->has_C) return fail(MMIDX_ERR_STATE, "coarse quantizer not loaded");
+    if (w < 1 || w > ix->p.nlist) return fail(MMIDX_ERR_W, "w = %d out of 1..nlist", w);
+    if (w > MMIDX_MAX_K) return fail(MMIDX_ERR_UNSUPPORTED, "w = %d exceeds %d", w, MMIDX_MAX_K);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int launches = 0;
+    const int64_t QC = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / ((size_t)ix->p.nlist * sizeof(double))));
+    for (int64_t q0 = 0; q0 < nq; q0 += QC) {
+        int64_t nb = std::min(QC, nq - q0);
+        Scratch sc(st);
+        RET(coarse_probe_dev(ix, dQ + q0 * ix->p.d, nb, w, d_out + q0 * w, sc, st, &launches));
+    }
     return MMIDX_OK;
 }
 

@@ -50,7 +50,8 @@ def _worker(rank, world, port, q):
             sh.loadCoarseQuantizer(Cq)
             sh.loadProductQuantizer(P)
             sh.setW(w)
-            lists, codes = sh.indexVectors(None, X, return_codes=True)
+            # "plain": default l % G ownership; "ties": load-balanced list -> shard map (mmidx_set_shard_map)
+            lists, codes = sh.indexVectors(None, X, return_codes=True) if case == "plain" else sh.indexVectorsBalanced(X)
             dQ = torch.from_numpy(Q).cuda()
             iids, dd, cnt = sh.search(k, dQ)
             off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
