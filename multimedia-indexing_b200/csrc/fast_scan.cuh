@@ -173,6 +173,19 @@ __global__ void k_apply_order(const uint8_t *__restrict__ codes, const int32_t *
     }
 }
 
+// One descriptor per (query, owned probe slot): everything the scan kernel needs about a probe in one place, so a
+// probe costs one independent 16-byte load instead of a chain of four dependent ones (oprobes -> probes -> list_off /
+// list_len -> sall).  Followed in memory by the m floats s[q][probe][j]; stride = fast_desc_stride(m) bytes.
+struct __align__(16) ProbeHdr {
+    long long start;  // first position of the list in the CSR arrays
+    int len;          // > 0
+    int p;            // probe rank (offer order of the queue, IVFPQ.java:414)
+    int l;            // coarse centroid / list id
+    int pad[3];
+};
+static_assert(sizeof(ProbeHdr) == 32, "ProbeHdr layout");
+__host__ __device__ constexpr int fast_desc_stride(int m) { return (int)sizeof(ProbeHdr) + 4 * m; }
+
 struct FastArgs {
     const double *Q;          // [nq][d]
     const double *C;          // [nlist][d]
@@ -190,11 +203,11 @@ struct FastArgs {
     const int32_t *orank;     // insertion rank (= offer order inside the list) of every reordered entry
     const int64_t *list_off;
     const int32_t *list_len;
-    const float *sall;        // [nq][w][m]  s[q][probe][j] (k_fast_prep)
     const double *bq;         // [nq]        error radius of the fp32 distances of query q (k_fast_prep)
     const float *T2;          // [nq][m*256] per-query term of the table decomposition (k_fast_t2)
     const int32_t *oprobes;   // [nq][w]     ranks of the probes with a non-empty list on this shard, ascending
     const int32_t *ocnt;      // [nq]
+    const unsigned char *desc;  // [nq][w] probe descriptors in oprobes order (ProbeHdr + s[m]), k_fast_prep
     int d, m, ks, S, w, k, nsplit;
     int resolve_ties;           // 1: replay the queue's tie rule inside the kernel (unsharded, nsplit == 1)
     int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
@@ -219,7 +232,9 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 // ADC table entry of sub-quantizer J for byte I of a packed code word (ks == 256: 1 KiB per sub-table)
-#define MMIDX_LK(J, word, I) lut[(J) * 256 + __byte_perm((word), 0, 0x4440 | (I))]
+#define MMIDX_LK(J, word, I) lds_f32<(J) * 1024>(lut + (__byte_perm((word), 0, 0x4440 | (I)) << 2))
+
+constexpr int FAST_POS_BITS = 22;  // lists longer than 2^22 entries disable the fast path (host check); w <= 1024
 
 // CTA-wide collector on fp32 keys with an error-band slack (see the header comment).
 template <int CAP>
@@ -232,6 +247,7 @@ struct TopK32 {
     unsigned int hist[256];
     float thr32;  // admission threshold: candidates with d32 > thr32 are provably outside the result
     int cnt, overflow;
+    int ovf;  // a barrier-free list scan ran out of slots: its entries are dropped and the list is scanned again
     int s_bin, s_krem, s_newcnt;
 
     __device__ __forceinline__ void init() {
@@ -239,6 +255,70 @@ struct TopK32 {
             thr32 = __int_as_float(0x7f800000);
             cnt = 0;
             overflow = 0;
+            ovf = 0;
+        }
+        __syncthreads();
+    }
+
+    // Barrier-free scan: both candidates of one 128-bit load (p1 == false for a single candidate); all 32 lanes of a
+    // converged warp.  There is no capacity guarantee here: entries past CAP are not stored and `ovf` is raised; every
+    // slot below min(cnt, CAP) still holds a valid entry, so drop_tag() can undo the list.
+    __device__ __forceinline__ void push2(bool p0, float d0, bool p1, float d1, unsigned int packed0) {
+        const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+        const int lane = threadIdx.x & 31;
+        const int n0 = __popc(m0), tot = n0 + __popc(m1);
+        int base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&cnt, tot);
+            if (base + tot > CAP) ovf = 1;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (p0) {
+            const int slot = base + __popc(m0 & lt);
+            if (slot < CAP) {
+                key[slot] = d0;
+                pk[slot] = packed0;
+            }
+        }
+        if (p1) {
+            const int slot = base + n0 + __popc(m1 & lt);
+            if (slot < CAP) {
+                key[slot] = d1;
+                pk[slot] = packed0 + 1u;
+            }
+        }
+    }
+
+    // remove every entry of probe slot `tag` (after an overflowed barrier-free scan); all threads, block-uniform
+    __device__ __noinline__ void drop_tag(unsigned int tag) {
+        const int tid = threadIdx.x;
+        const int n = min(cnt, CAP);
+        float d[PER];
+        unsigned int pp[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = tid + e * MMIDX_NT;
+            if (i < n) {
+                d[e] = key[i];
+                pp[e] = pk[i];
+            }
+        }
+        if (tid == 0) s_newcnt = 0;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = tid + e * MMIDX_NT;
+            if (i < n && (pp[e] >> FAST_POS_BITS) != tag) {
+                const int slot = atomicAdd(&s_newcnt, 1);
+                key[slot] = d[e];
+                pk[slot] = pp[e];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            cnt = s_newcnt;
+            ovf = 0;
         }
         __syncthreads();
     }
@@ -319,7 +399,7 @@ struct TopK32 {
     }
 
     // keep every entry at or below the slack line of the k-th smallest key
-    __device__ void compact(int k, double bq, double rel) {
+    __device__ __noinline__ void compact(int k, double bq, double rel) {
         const int tid = threadIdx.x;
         const int n = cnt;
         const float kth = select_kth(n, k);
@@ -382,42 +462,11 @@ __device__ __forceinline__ double exact_adc(const double *__restrict__ Cl, const
     return dist;
 }
 
-// The same value computed by one warp with coalesced loads: lane <-> term (j, t); the squared terms are staged
-// in shared memory (xs[m][S+1]) and summed in index order by lane j, then lane 0 adds the m sub-sums in order.
-// Returns the distance in every lane.  xs is private to the warp.
-__device__ __forceinline__ double exact_adc_warp(const double *__restrict__ Cl, const double *__restrict__ qv,
-                                                 const int32_t *__restrict__ perm, const double *__restrict__ P,
-                                                 const uint8_t *__restrict__ code, int m, int ks, int S,
-                                                 double *xs) {
-    const int lane = threadIdx.x & 31;
-    const int d = m * S;
-    const int sh = ((S & (S - 1)) == 0) ? (31 - __clz(S)) : -1;
-    for (int e = lane; e < d; e += 32) {
-        const int j = (sh >= 0) ? (e >> sh) : (e / S);
-        const int t = e - j * S;
-        int src = e;
-        if (perm) src = perm[src];
-        const double r = __dsub_rn(Cl[src], qv[src]);
-        const double p = P[((int64_t)j * ks + code[j]) * S + t];
-        const double a = __dsub_rn(r, p);
-        xs[j * (S + 1) + t] = __dmul_rn(a, a);
-    }
-    __syncwarp();
-    double acc = 0.0;
-    if (lane < m)
-        for (int t = 0; t < S; ++t) acc = __dadd_rn(acc, xs[lane * (S + 1) + t]);
-    double dist = 0.0;
-    for (int j = 0; j < m; ++j) dist = __dadd_rn(dist, __shfl_sync(0xffffffffu, acc, j));
-    __syncwarp();
-    return dist;
-}
-
 template <int CAP32>
 struct FastExactCap {
     static constexpr int value = 512;  // exact collector for the survivors; more survivors than this -> direct kernel
 };
 
-constexpr int FAST_POS_BITS = 22;  // lists longer than 2^22 entries disable the fast path (host check)
 
 // T2[q][j*256 + c] = 2 * sum_t q32[perm(jS+t)] * P32t[j][t][c]: the per-query term of the table decomposition, for
 // a whole batch.  grid (ceil(nq / T2_QB), m), thread <-> c; the thread keeps its S codebook values in registers and
@@ -462,16 +511,18 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_t2(const double *__restrict__
     }
 }
 
-// Per-query pre-pass: s[q][p][j] = sum_t q_t (q_t - 2 C_l,t) over the (permuted) sub-vector j of probe p, in
-// binary64 then rounded to fp32, and the error radius Bq of the query (header comment).  grid nq.
+// Per-query pre-pass.  For every probe whose list is non-empty on this shard, in probe-rank order: a ProbeHdr and
+// s[j] = sum_t q_t (q_t - 2 C_l,t) over the (permuted) sub-vector j, in binary64 then rounded to fp32; and the
+// error radius Bq of the query (header comment).  grid nq.
 // MT/ST > 0: compile-time m and S (S a power of two <= 32: S consecutive lanes share one (probe, j) pair and read
 // the centroid sub-vector as one contiguous segment); 0: generic.
 template <int MT, int ST>
 __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict__ Q, const double *__restrict__ C,
                                                         const int32_t *__restrict__ perm, const int32_t *__restrict__ probes,
                                                         const float *__restrict__ t1max, const float *__restrict__ pmax,
+                                                        const int64_t *__restrict__ list_off,
                                                         const int32_t *__restrict__ list_len, int d, int m_rt, int S_rt,
-                                                        int w, float *__restrict__ sall, double *__restrict__ bq,
+                                                        int w, unsigned char *__restrict__ desc, double *__restrict__ bq,
                                                         int32_t *__restrict__ oprobes, int32_t *__restrict__ ocnt) {
     const int m = MT > 0 ? MT : m_rt;
     const int S = ST > 0 ? ST : S_rt;
@@ -479,8 +530,11 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
     double *qv = reinterpret_cast<double *>(smem_raw);  // [d]
     float *qn = reinterpret_cast<float *>(qv + d);      // [m]  upper bound of ||q_j||
     float *bterm = qn + m;                              // [m]
+    int *slot_of = reinterpret_cast<int *>(bterm + m);  // [w]  descriptor slot of probe rank p, -1: not on this shard
     const int tid = threadIdx.x;
     const int64_t q = blockIdx.x;
+    const int dstride = fast_desc_stride(m);
+    unsigned char *dq = desc + q * (int64_t)w * dstride;
     for (int i = tid; i < d; i += MMIDX_NT) qv[i] = Q[q * (int64_t)d + i];
     if (tid < m) bterm[tid] = 0.f;
     __syncthreads();
@@ -493,7 +547,6 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
         }
         qn[tid] = __fsqrt_ru(__double2float_ru(n2 * (1.0 + 1e-12)));
     }
-    __syncthreads();
     const int32_t *pr = probes + q * w;
     const double cS = 4.0 * S + 14.0;
     // probe ranks with a non-empty list on this shard, in rank order (lists other shards own have length 0 here)
@@ -501,13 +554,31 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
         int base = 0;
         for (int p0 = 0; p0 < w; p0 += 32) {
             const int p = p0 + tid;
-            const bool own = p < w && list_len[pr[p]] > 0;
+            int l = 0, len = 0;
+            if (p < w) {
+                l = pr[p];
+                len = list_len[l];
+            }
+            const bool own = len > 0;
             const unsigned mk = __ballot_sync(0xffffffffu, own);
-            if (own) oprobes[q * w + base + __popc(mk & ((1u << tid) - 1u))] = p;
+            if (p < w) slot_of[p] = -1;
+            if (own) {
+                const int slot = base + __popc(mk & ((1u << tid) - 1u));
+                slot_of[p] = slot;
+                oprobes[q * w + slot] = p;
+                ProbeHdr h;
+                h.start = list_off[l];
+                h.len = len;
+                h.p = p;
+                h.l = l;
+                h.pad[0] = h.pad[1] = h.pad[2] = 0;
+                *reinterpret_cast<ProbeHdr *>(dq + (int64_t)slot * dstride) = h;
+            }
             base += __popc(mk);
         }
         if (tid == 0) ocnt[q] = base;
     }
+    __syncthreads();
     if (ST > 0) {
         const int lane = tid & 31, warp = tid >> 5;
         constexpr int SS = ST > 0 ? ST : 1;
@@ -518,7 +589,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
             const bool valid = e < w * m;
             const int p = valid ? e / m : 0, j = valid ? e - p * m : 0;
             const int l = pr[p];
-            const bool use = valid && list_len[l] > 0;
+            const int slot = slot_of[p];
+            const bool use = valid && slot >= 0;
             int src = j * S + t;
             if (perm) src = perm[src];
             const double qt = qv[src];
@@ -526,7 +598,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
 #pragma unroll
             for (int o = SS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (use && t == 0) {
-                sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
+                reinterpret_cast<float *>(dq + (int64_t)slot * dstride + sizeof(ProbeHdr))[j] = __double2float_rn(acc);
                 const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + cS * (double)qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
                 atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
             }
@@ -535,7 +607,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
         for (int e = tid; e < w * m; e += MMIDX_NT) {
             const int p = e / m, j = e - p * m;
             const int l = pr[p];
-            if (list_len[l] <= 0) continue;
+            const int slot = slot_of[p];
+            if (slot < 0) continue;
             const double *Cl = C + (int64_t)l * d;
             double acc = 0.0;
             for (int t = 0; t < S; ++t) {
@@ -544,7 +617,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
                 const double qt = qv[src];
                 acc += qt * (qt - 2.0 * Cl[src]);
             }
-            sall[q * (int64_t)w * m + e] = __double2float_rn(acc);
+            reinterpret_cast<float *>(dq + (int64_t)slot * dstride + sizeof(ProbeHdr))[j] = __double2float_rn(acc);
             const double term = 3.0 * (double)t1max[(int64_t)l * m + j] + cS * (double)qn[j] * (double)pmax[j] + 2.0 * fabs(acc);
             atomicMax(reinterpret_cast<int *>(&bterm[j]), __float_as_int(__double2float_ru(term)));
         }
@@ -557,38 +630,125 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
     }
 }
 
-// grid (nsplit, nq).  CTA (s, q) handles probes s, s+nsplit, ... of query q in rank order.
-// Shared memory: TopK32 | t2 | stage (TMA target: T1 row of the next probe) | lut[2] | qv.  The only block-wide
-// barriers in the probe loop are the collector's round barriers: the table of probe p+1 is built into the
-// other lut buffer, and `stage` is refilled right after the first round barrier of each probe.
+// ---- packed fp32 pairs (Blackwell add.f32x2, SASS FADD2): one issue slot adds both candidates of a 128-bit load ----
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long x, unsigned long long y) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// fp32 ADC sums of the code word(s) of one 128-bit load; `lut` is the 32-bit shared-window address of the table.  M == 8: two candidates (c.xy, c.zw), d0/d1 are their sums,
+// terms added for j ascending.  M == 16: one candidate, d0 = the sum (even-j and odd-j chains added last), d1 unused.
+template <int M>
+__device__ __forceinline__ void adc_pair(const uint32_t lut, const uint4 c, float &d0, float &d1) {
+    unsigned long long acc;
+    if (M == 8) {
+        acc = f2_pack(MMIDX_LK(0, c.x, 0), MMIDX_LK(0, c.z, 0));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(1, c.x, 1), MMIDX_LK(1, c.z, 1)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(2, c.x, 2), MMIDX_LK(2, c.z, 2)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(3, c.x, 3), MMIDX_LK(3, c.z, 3)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(4, c.y, 0), MMIDX_LK(4, c.w, 0)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(5, c.y, 1), MMIDX_LK(5, c.w, 1)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(6, c.y, 2), MMIDX_LK(6, c.w, 2)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(7, c.y, 3), MMIDX_LK(7, c.w, 3)));
+        f2_unpack(acc, d0, d1);
+    } else {
+        acc = f2_pack(MMIDX_LK(0, c.x, 0), MMIDX_LK(1, c.x, 1));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(2, c.x, 2), MMIDX_LK(3, c.x, 3)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(4, c.y, 0), MMIDX_LK(5, c.y, 1)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(6, c.y, 2), MMIDX_LK(7, c.y, 3)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(8, c.z, 0), MMIDX_LK(9, c.z, 1)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(10, c.z, 2), MMIDX_LK(11, c.z, 3)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(12, c.w, 0), MMIDX_LK(13, c.w, 1)));
+        acc = f2_add(acc, f2_pack(MMIDX_LK(14, c.w, 2), MMIDX_LK(15, c.w, 3)));
+        float lo, hi;
+        f2_unpack(acc, lo, hi);
+        d0 = lo + hi;
+        d1 = 0.f;
+    }
+}
+
+// One list with a block barrier per ROUND candidates: the collector can never run out of slots.  Used while the
+// admission threshold is still +inf (everything is pushed) and to redo a list whose barrier-free scan overflowed.
+template <int CAP32, int M>
+__device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t lut, const uint8_t *__restrict__ lc, int len,
+                                 unsigned int ptag, int k, double bq, double rel) {
+    constexpr int ROUND = TopK32<CAP32>::ROUND;
+    constexpr int CPT = (M == 8) ? 2 : 1;         // candidates per 128-bit load
+    constexpr int NE = ROUND / (MMIDX_NT * CPT);  // loads per thread per round
+    const int tid = threadIdx.x;
+    for (int base = 0; base < len; base += ROUND) {
+        c32.maybe_compact(k, bq, rel);  // round barrier
+        const float thr32 = c32.thr32;
+        uint4 cw[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int i0 = base + (e * MMIDX_NT + tid) * CPT;
+            cw[e] = make_uint4(0, 0, 0, 0);
+            if (i0 < len) cw[e] = ld_nc_u4(lc + (int64_t)i0 * M);
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            // warp-uniform skip of the list tail (push() only synchronises within the warp)
+            if (base + (e * MMIDX_NT + (tid & ~31)) * CPT >= len) continue;
+            const int i0 = base + (e * MMIDX_NT + tid) * CPT;
+            float d0, d1;
+            adc_pair<M>(lut, cw[e], d0, d1);
+            c32.push((i0 < len) && d0 <= thr32, d0, ptag | (unsigned int)i0);
+            if (M == 8) c32.push((i0 + 1 < len) && d1 <= thr32, d1, ptag | (unsigned int)(i0 + 1));
+        }
+    }
+    __syncthreads();  // every push of this list is visible
+}
+
+// grid (nsplit, nq).  CTA (s, q) handles owned probe slots s, s+nsplit, ... of query q in rank order.
+// Shared memory: TopK32 | t2 | stage (TMA target: T1 row of the next probe) | lut[2] | qv.
+// Per probe: one independent descriptor load, the fp32 table lut = (T1[l] + T2) + s built with 128-bit shared accesses
+// into the buffer the previous probe is not using, ONE block barrier (which also settles the collector), the TMA for
+// the next T1 row, then a barrier-free sweep over the list with the next 128-bit code load in flight.
 template <int CAP32, int M>
 __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
     constexpr int ECAP = FastExactCap<CAP32>::value;
     constexpr int ks = 256;  // the fused kernel is specialised for full byte codes (host checks ks == 256)
     constexpr int nent = M * ks;
+    constexpr int NV = nent / (4 * MMIDX_NT);  // float4 entries of one table per thread
+    constexpr int DSTRIDE = fast_desc_stride(M);
+    constexpr int KEEP = TopK32<CAP32>::KEEP_MAX;
+    constexpr unsigned POS_MASK = (1u << FAST_POS_BITS) - 1u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TopK32<CAP32> &c32 = *reinterpret_cast<TopK32<CAP32> *>(smem_raw);
     const size_t c32_bytes = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
-    // region A (scan phase): t2 | stage | lut0 | lut1.   Aliased in the final phase by: TopK<ECAP> | per-warp xs
+    // region A (scan phase): t2 | stage | lut0 | lut1.   Aliased in the final phase by: TopK<ECAP> | s_l | xs
     unsigned char *regA = smem_raw + c32_bytes;
     float *t2 = reinterpret_cast<float *>(regA);   // [nent]
     float *stage = t2 + nent;                      // [nent]
     float *lut0 = stage + nent;                    // [nent]
     float *lut1 = lut0 + nent;                     // [nent]
+    const uint32_t lut0_s = smem_u32(lut0), lut1_s = smem_u32(lut1);
     const size_t tk_bytes = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
-    const size_t xs_bytes = (size_t)(MMIDX_NT / 32) * M * (a.S + 1) * sizeof(double);
-    const size_t regA_bytes = max((size_t)4 * nent * sizeof(float), tk_bytes + xs_bytes);
+    // final phase needs room for at least one survivor's terms (host: fast_smem_bytes)
+    const size_t fin_bytes = tk_bytes + ECAP * sizeof(int) + (size_t)M * (a.S + 1) * sizeof(double);
+    const size_t regA_bytes = max((size_t)4 * nent * sizeof(float), fin_bytes);
     double *qv = reinterpret_cast<double *>(regA + ((regA_bytes + 15) & ~(size_t)15));  // [d] raw query
     uint64_t *bars = reinterpret_cast<uint64_t *>(qv + a.d);                            // [1]
 
     const int tid = threadIdx.x;
     const int s = blockIdx.x;
     const int64_t q = blockIdx.y;
-    const int32_t *pr = a.probes + q * a.w;
+    const unsigned char *dq = a.desc + q * (int64_t)a.w * DSTRIDE;
     const uint32_t t1_bytes = (uint32_t)(nent * sizeof(float));
     const int S = a.S;
     const double rel = (double)M * 5.9604644775390625e-08;
     const double bq = a.bq[q];
+    const float finf = __int_as_float(0x7f800000);
 
     c32.init();
     if (tid == 0) {
@@ -597,138 +757,179 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     }
     for (int i = tid; i < a.d; i += MMIDX_NT) qv[i] = a.Q[q * (int64_t)a.d + i];
     __syncthreads();
-    const int32_t *op = a.oprobes + q * a.w;  // probe ranks this CTA's shard really has to scan
     const int nop = a.ocnt[q];
     if (tid == 0 && s < nop) {
+        const int l0 = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)s * DSTRIDE)->l;
         mbar_arrive_expect_tx(&bars[0], t1_bytes);
-        tma_load_1d(stage, a.T1 + (int64_t)pr[op[s]] * nent, t1_bytes, &bars[0]);
+        tma_load_1d(stage, a.T1 + (int64_t)l0 * nent, t1_bytes, &bars[0]);
     }
-    // ---- per-query prologue: this query's T2 row (k_fast_t2) into shared memory ----
+    // ---- per-query prologue: this query's T2 row (k_fast_t2) into shared memory.  Thread tid owns the float4
+    //      entries tid + 256*r of every table (t2, stage, lut): it only ever re-reads what it wrote itself. ----
+    float4 *t2v = reinterpret_cast<float4 *>(t2);
+    const float4 *stv = reinterpret_cast<const float4 *>(stage);
     {
-        const float *t2g = a.T2 + q * (int64_t)nent;
+        const float4 *t2g = reinterpret_cast<const float4 *>(a.T2 + q * (int64_t)nent);
 #pragma unroll
-        for (int j = 0; j < M; ++j) t2[tid + 256 * j] = t2g[tid + 256 * j];
+        for (int r = 0; r < NV; ++r) t2v[tid + MMIDX_NT * r] = t2g[tid + MMIDX_NT * r];
     }
-    // (t2 is published by the first round barrier below; each thread only re-reads the entries it wrote
-    //  in the table build, which uses the same e = tid + 256*i mapping)
 
-    unsigned long long n_cand = 0;
+    // Settles the collector at a block barrier: if the barrier-free scan of slot `pslot` overflowed, its entries are
+    // dropped and the list is scanned again with round barriers from its (still intact) table `plut`; then the buffer
+    // is compacted when it is more than half full, or to get a first finite threshold.
+    auto settle = [&](int pslot, const uint32_t plut) {
+        const int need = (c32.ovf != 0) | (*(volatile int *)&c32.cnt > KEEP) |
+                         ((c32.thr32 == finf) & (*(volatile int *)&c32.cnt >= a.k));
+        if (__syncthreads_or(need)) {
+            const int ov = c32.ovf;
+            __syncthreads();
+            if (ov) {  // block-uniform
+                c32.drop_tag((unsigned int)pslot);
+                const ProbeHdr *h = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)pslot * DSTRIDE);
+                scan_list_rounds<CAP32, M>(c32, plut, a.ocodes + h->start * M, h->len, ((unsigned int)pslot) << FAST_POS_BITS,
+                                           a.k, bq, rel);
+            }
+            const int n = c32.cnt;
+            const bool isinf32 = c32.thr32 == finf;
+            __syncthreads();  // everybody has read the state before the next list starts pushing
+            if (n >= a.k && (n > KEEP || isinf32)) c32.compact(a.k, bq, rel);
+        }
+    };
+
     int it = 0;
     for (int ii = s; ii < nop; ii += a.nsplit, ++it) {
         float *lut = (it & 1) ? lut1 : lut0;
-        const int p = op[ii];
-        const int l = pr[p];
-        const int64_t start = a.list_off[l];
-        const int len = a.list_len[l];  // > 0 by construction of oprobes
-        mbar_wait(&bars[0], (uint32_t)(it & 1));
-        // ADC table of this probe: lut = T1[l] + T2 + s   (thread tid owns entries tid + 256*j, i.e. one per j)
-        {
-            const float *sp = a.sall + (q * (int64_t)a.w + p) * M;
+        const uint32_t lut_s = (it & 1) ? lut1_s : lut0_s;
+        const unsigned char *dp = dq + (int64_t)ii * DSTRIDE;
+        const int4 hd = *reinterpret_cast<const int4 *>(dp);  // start (lo, hi), len, probe rank
+        float sj[NV];
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
-                const int e = tid + 256 * j;
-                lut[e] = (stage[e] + t2[e]) + sp[j];
+        for (int r = 0; r < NV; ++r) sj[r] = reinterpret_cast<const float *>(dp + sizeof(ProbeHdr))[(tid + MMIDX_NT * r) >> 6];
+        int lnext = 0;
+        if (tid == 0 && ii + a.nsplit < nop) lnext = reinterpret_cast<const ProbeHdr *>(dp + (int64_t)a.nsplit * DSTRIDE)->l;
+        const int64_t start = (int64_t)(((unsigned long long)(unsigned int)hd.y << 32) | (unsigned long long)(unsigned int)hd.x);
+        const int len = hd.z;  // > 0 by construction of the descriptors
+        mbar_wait(&bars[0], (uint32_t)(it & 1));
+        // ADC table of this probe: lut = (T1[l] + T2) + s
+        {
+            float4 *lutv = reinterpret_cast<float4 *>(lut);
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {
+                const int e4 = tid + MMIDX_NT * r;
+                const float4 sv = stv[e4], tv = t2v[e4];
+                float4 ov;
+                ov.x = (sv.x + tv.x) + sj[r];
+                ov.y = (sv.y + tv.y) + sj[r];
+                ov.z = (sv.z + tv.z) + sj[r];
+                ov.w = (sv.w + tv.w) + sj[r];
+                lutv[e4] = ov;
             }
+        }
+        // the probe's barrier: publishes the table, ends every read of `stage` and every push of the previous list
+        settle(ii - a.nsplit, (it & 1) ? lut0_s : lut1_s);
+        if (tid == 0 && ii + a.nsplit < nop) {
+            // every thread has consumed `stage`: the next probe's T1 row lands while this list is scanned
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bars[0], t1_bytes);
+            tma_load_1d(stage, a.T1 + (int64_t)lnext * nent, t1_bytes, &bars[0]);
         }
         const uint8_t *lc = a.ocodes + start * M;
-        const unsigned int ptag = ((unsigned int)p) << FAST_POS_BITS;
-        constexpr int ROUND = TopK32<CAP32>::ROUND;
-        constexpr int CPT = (M == 8) ? 2 : 1;              // candidates per 128-bit load
-        constexpr int NE = ROUND / (MMIDX_NT * CPT);       // loads per thread per round
-        for (int base = 0; base < len || base == 0; base += ROUND) {
-            c32.maybe_compact(a.k, bq, rel);  // round barrier: publishes the table, ends the previous probe's reads
-            if (base == 0 && tid == 0 && ii + a.nsplit < nop) {
-                // every thread has consumed `stage`: the next probe's T1 row lands while this list is scanned
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&bars[0], t1_bytes);
-                tma_load_1d(stage, a.T1 + (int64_t)pr[op[ii + a.nsplit]] * nent, t1_bytes, &bars[0]);
-            }
-            if (base >= len) break;
-            const float thr32 = c32.thr32;
-            uint4 cw[NE];
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {  // all loads of the round in flight before the first lookup
-                const int i0 = base + (e * MMIDX_NT + tid) * CPT;
-                cw[e] = make_uint4(0, 0, 0, 0);
-                if (i0 < len) cw[e] = ld_nc_u4(lc + (int64_t)i0 * M);
-            }
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                // warp-uniform skip of the list tail (push() only synchronises within the warp)
-                if (base + (e * MMIDX_NT + (tid & ~31)) * CPT >= len) continue;
-                const int i0 = base + (e * MMIDX_NT + tid) * CPT;
-                const uint4 c = cw[e];
-                if (M == 8) {
-                    float d0 = MMIDX_LK(0, c.x, 0);
-                    float d1 = MMIDX_LK(0, c.z, 0);
-                    d0 += MMIDX_LK(1, c.x, 1);
-                    d1 += MMIDX_LK(1, c.z, 1);
-                    d0 += MMIDX_LK(2, c.x, 2);
-                    d1 += MMIDX_LK(2, c.z, 2);
-                    d0 += MMIDX_LK(3, c.x, 3);
-                    d1 += MMIDX_LK(3, c.z, 3);
-                    d0 += MMIDX_LK(4, c.y, 0);
-                    d1 += MMIDX_LK(4, c.w, 0);
-                    d0 += MMIDX_LK(5, c.y, 1);
-                    d1 += MMIDX_LK(5, c.w, 1);
-                    d0 += MMIDX_LK(6, c.y, 2);
-                    d1 += MMIDX_LK(6, c.w, 2);
-                    d0 += MMIDX_LK(7, c.y, 3);
-                    d1 += MMIDX_LK(7, c.w, 3);
-                    c32.push((i0 < len) && d0 <= thr32, d0, ptag | (unsigned int)i0);
-                    c32.push((i0 + 1 < len) && d1 <= thr32, d1, ptag | (unsigned int)(i0 + 1));
-                } else {
-                    float d0 = MMIDX_LK(0, c.x, 0);
-                    float d1 = MMIDX_LK(1, c.x, 1);
-                    d0 += MMIDX_LK(2, c.x, 2);
-                    d1 += MMIDX_LK(3, c.x, 3);
-                    d0 += MMIDX_LK(4, c.y, 0);
-                    d1 += MMIDX_LK(5, c.y, 1);
-                    d0 += MMIDX_LK(6, c.y, 2);
-                    d1 += MMIDX_LK(7, c.y, 3);
-                    d0 += MMIDX_LK(8, c.z, 0);
-                    d1 += MMIDX_LK(9, c.z, 1);
-                    d0 += MMIDX_LK(10, c.z, 2);
-                    d1 += MMIDX_LK(11, c.z, 3);
-                    d0 += MMIDX_LK(12, c.w, 0);
-                    d1 += MMIDX_LK(13, c.w, 1);
-                    d0 += MMIDX_LK(14, c.w, 2);
-                    d1 += MMIDX_LK(15, c.w, 3);
-                    d0 += d1;
-                    c32.push((i0 < len) && d0 <= thr32, d0, ptag | (unsigned int)i0);
-                }
+        const unsigned int ptag = ((unsigned int)ii) << FAST_POS_BITS;
+        const float thr32 = c32.thr32;
+        if (thr32 == finf) {  // block-uniform: nothing can be rejected yet
+            scan_list_rounds<CAP32, M>(c32, lut_s, lc, len, ptag, a.k, bq, rel);
+        } else {
+            constexpr int CPT = (M == 8) ? 2 : 1;
+            constexpr int STEP = MMIDX_NT * CPT;
+            int i0 = tid * CPT;
+            uint4 cur = make_uint4(0, 0, 0, 0);
+            if (i0 < len) cur = ld_nc_u4(lc + (int64_t)i0 * M);
+            for (int wb = (tid & ~31) * CPT; wb < len; wb += STEP) {  // warp-uniform trip count
+                const int i1 = i0 + STEP;
+                uint4 nxt = make_uint4(0, 0, 0, 0);
+                if (i1 < len) nxt = ld_nc_u4(lc + (int64_t)i1 * M);
+                float d0, d1;
+                adc_pair<M>(lut_s, cur, d0, d1);
+                const bool p0 = (i0 < len) && d0 <= thr32;
+                const bool p1 = (M == 8) && (i0 + 1 < len) && d1 <= thr32;
+                if (__any_sync(0xffffffffu, p0 | p1)) c32.push2(p0, d0, p1, d1, ptag | (unsigned int)i0);
+                cur = nxt;
+                i0 = i1;
             }
         }
-        n_cand += (unsigned long long)len;
     }
+    if (it > 0) settle(s + (it - 1) * a.nsplit, ((it - 1) & 1) ? lut1_s : lut0_s);
 
     // ---- final phase: shrink to the error band, evaluate the survivors exactly, exact top-k ----
     __syncthreads();
     const int n_before = c32.cnt;
+    __syncthreads();
     if (n_before > a.k) c32.compact(a.k, bq, rel);
     const int nsurv = c32.cnt;
     const bool overflow = c32.overflow != 0 || nsurv > ECAP;
     TopK<ECAP> &tk = *reinterpret_cast<TopK<ECAP> *>(regA);  // aliases t2/stage/lut: no TMA is in flight any more
-    double *xs = reinterpret_cast<double *>(regA + tk_bytes) + (size_t)(tid >> 5) * M * (S + 1);
+    int *s_l = reinterpret_cast<int *>(regA + tk_bytes);                      // [ECAP] list id of every survivor
+    double *xs = reinterpret_cast<double *>(regA + tk_bytes + ECAP * sizeof(int));  // [NB][M][S + 1] squared terms
+    uint8_t *scode = reinterpret_cast<uint8_t *>(c32.key);                    // [ECAP][M]; the fp32 keys are dead now
+    static_assert(sizeof(c32.key) >= (size_t)ECAP * M, "survivor codes are staged in the fp32 key array");
     tk.init();
     if (!overflow) {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int base = 0; base < nsurv; base += MMIDX_NT / 32) {
-            const int e = base + warp;  // warp-uniform
-            double dv = 0.0;
-            unsigned long long sq = 0ull;
-            int pay = 0;
-            if (e < nsurv) {
-                const unsigned int packed = c32.pk[e];
-                const int pb = (int)(packed >> FAST_POS_BITS);
-                const int l = pr[pb];
-                const int64_t ps = a.list_off[l] + (int64_t)(packed & ((1u << FAST_POS_BITS) - 1u));
-                dv = exact_adc_warp(a.C + (int64_t)l * a.d, qv, a.perm, a.P, a.ocodes + ps * M, M, ks, S, xs);
-                sq = (((unsigned long long)pb) << 32) | (unsigned long long)a.orank[ps];
-                pay = a.oiids[ps];
-            }
-            tk.push(e < nsurv && lane == 0, dv, sq, pay);
+        // Exact binary64 distance of every survivor in the reference's operation order (computeResidualVector
+        // IVFPQ.java:642-648, computeLookupADC :525-538, ADC sum :435-438).
+        // A: one thread per survivor gathers its code, list id, offer sequence and iid (slot e of the exact collector).
+        for (int e = tid; e < nsurv; e += MMIDX_NT) {
+            const unsigned int packed = c32.pk[e];
+            const ProbeHdr *h = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)(packed >> FAST_POS_BITS) * DSTRIDE);
+            const int64_t ps = h->start + (int64_t)(packed & POS_MASK);
+            if (M == 8)
+                reinterpret_cast<uint2 *>(scode)[e] = *reinterpret_cast<const uint2 *>(a.ocodes + ps * M);
+            else
+                reinterpret_cast<uint4 *>(scode)[e] = *reinterpret_cast<const uint4 *>(a.ocodes + ps * M);
+            s_l[e] = h->l;
+            tk.seq[e] = (((unsigned long long)(unsigned int)h->p) << 32) | (unsigned long long)(unsigned int)a.orank[ps];
+            tk.pay[e] = a.oiids[ps];
         }
+        __syncthreads();
+        // B: batches of NB survivors.  thread <-> element (survivor, j, t) with coalesced loads of the centroid and
+        //    codebook rows: x = ((C_l - q) - P_j,c)[t]^2.  C: thread <-> (survivor, j) adds its S terms for t ascending
+        //    (= LUT[j][code_j]).  D: thread <-> survivor adds the m table entries for j ascending.
+        const int d = a.d;
+        const int row = S + 1;
+        const int NB = (int)((regA_bytes - tk_bytes - ECAP * sizeof(int)) / ((size_t)M * row * sizeof(double)));
+        const int shS = ((S & (S - 1)) == 0) ? (31 - __clz(S)) : -1;
+        const int shD = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
+        for (int b0 = 0; b0 < nsurv; b0 += NB) {
+            const int nb = min(NB, nsurv - b0);
+            const int total = nb * d;
+            for (int g = tid; g < total; g += MMIDX_NT) {
+                const int e = (shD >= 0) ? (g >> shD) : (g / d);
+                const int i = g - e * d;
+                const int j = (shS >= 0) ? (i >> shS) : (i / S);
+                const int t = i - j * S;
+                int src = i;
+                if (a.perm) src = a.perm[i];
+                const unsigned int code = scode[(b0 + e) * M + j];
+                const double r = __dsub_rn(a.C[(int64_t)s_l[b0 + e] * d + src], qv[src]);  // residual = centroid - query
+                const double df = __dsub_rn(r, a.P[((int64_t)j * ks + code) * S + t]);
+                xs[(e * M + j) * row + t] = __dmul_rn(df, df);
+            }
+            __syncthreads();
+            for (int item = tid; item < nb * M; item += MMIDX_NT) {
+                double *xr = xs + item * row;
+                double acc = 0.0;
+                for (int t = 0; t < S; ++t) acc = __dadd_rn(acc, xr[t]);
+                xr[S] = acc;
+            }
+            __syncthreads();
+            for (int e = tid; e < nb; e += MMIDX_NT) {
+                double dv = 0.0;
+#pragma unroll
+                for (int j = 0; j < M; ++j) dv = __dadd_rn(dv, xs[(e * M + j) * row + S]);
+                tk.dist[b0 + e] = dv;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) tk.cnt = nsurv;
+        __syncthreads();
     }
     // Exact ties cut at the k-th boundary: without overflow the survivors contain EVERY candidate with an exact
     // distance <= T (a candidate outside the band is strictly farther than T), so the queue's rule
@@ -769,6 +970,8 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
         }
     }
     if (a.stats && tid == 0) {
+        unsigned long long n_cand = 0;
+        for (int ii = s; ii < nop; ii += a.nsplit) n_cand += (unsigned long long)reinterpret_cast<const ProbeHdr *>(dq + (int64_t)ii * DSTRIDE)->len;
         atomicAdd(&a.stats[0], n_cand);
         atomicAdd(&a.stats[2], (unsigned long long)nsurv);
         if (overflow) atomicAdd(&a.stats[3], 1ull);

@@ -1081,6 +1081,7 @@ static bool fast_eligible(const mmidx_index *ix) {
     if (ix->p.type != MMIDX_IVFPQ || ix->force_exact) return false;
     // the fused kernel is specialised for byte codes with full 256-entry sub-tables and 8 or 16 sub-quantizers
     if (ix->p.ks != 256 || (ix->p.m != 8 && ix->p.m != 16)) return false;
+    if (ix->p.d > 2048) return false;  // query + one survivor's squared terms must fit next to the collectors
     return true;
 }
 
@@ -1112,8 +1113,8 @@ static size_t fast_smem_bytes(int ks, int S, int d) {
     constexpr int ECAP = FastExactCap<CAP32>::value;
     const size_t c32b = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
     const size_t tkb = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
-    const size_t xsb = (size_t)(MMIDX_NT / 32) * M * (S + 1) * sizeof(double);
-    size_t regA = std::max((size_t)4 * M * ks * sizeof(float), tkb + xsb);
+    const size_t finb = tkb + ECAP * sizeof(int) + (size_t)M * (S + 1) * sizeof(double);  // final phase of k_ivfpq_scan_fast
+    size_t regA = std::max((size_t)4 * M * ks * sizeof(float), finb);
     regA = (regA + 15) & ~(size_t)15;
     return c32b + regA + (size_t)d * 8 + 16 + 64;
 }
@@ -1158,23 +1159,23 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     a.stats = ix->want_stats ? ix->dstats.as<unsigned long long>() : nullptr;
     {
         // per-(query, probe) terms of the table decomposition and the per-query error radius
-        float *sall;
+        unsigned char *desc;
         double *bq;
         int32_t *oprobes, *ocnt;
         float *T2;
         RET(sc.get(&T2, (size_t)nq * M * 256));
-        RET(sc.get(&sall, (size_t)nq * w * M));
+        RET(sc.get(&desc, (size_t)nq * w * fast_desc_stride(M)));
         RET(sc.get(&bq, (size_t)nq));
         RET(sc.get(&oprobes, (size_t)nq * w));
         RET(sc.get(&ocnt, (size_t)nq));
         StageMark sm(ix, st, 1);
-        const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)M * 4 + 16;
+        const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)w * 4 + 16;
         if (M == 8 && a.S == 16)
-            k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_len, a.d, M, a.S, w, sall, bq, oprobes, ocnt);
+            k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, desc, bq, oprobes, ocnt);
         else if (M == 16 && a.S == 8)
-            k_fast_prep<16, 8><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_len, a.d, M, a.S, w, sall, bq, oprobes, ocnt);
+            k_fast_prep<16, 8><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, desc, bq, oprobes, ocnt);
         else
-            k_fast_prep<0, 0><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_len, a.d, M, a.S, w, sall, bq, oprobes, ocnt);
+            k_fast_prep<0, 0><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, desc, bq, oprobes, ocnt);
         RET(post_launch("k_fast_prep", launches));
         {
             dim3 g2((unsigned)((nq + T2_QB - 1) / T2_QB), M);
@@ -1188,7 +1189,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
             RET(post_launch("k_fast_t2", launches));
         }
         a.T2 = T2;
-        a.sall = sall;
+        a.desc = desc;
         a.bq = bq;
         a.oprobes = oprobes;
         a.ocnt = ocnt;
