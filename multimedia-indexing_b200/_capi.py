@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmidx.so")
+# MMIDX_LIB_PATH: development override used by the kernel-variant sweeps under profiles/ (still a CUDA build of csrc/)
+LIB_PATH = os.environ.get("MMIDX_LIB_PATH") or os.path.join(_HERE, "libmmidx.so")
 
 MMIDX_LINEAR, MMIDX_PQ, MMIDX_IVFPQ = 0, 1, 2
 OK, ERR_INVALID, ERR_DIM, ERR_FULL, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED, ERR_W = range(8)

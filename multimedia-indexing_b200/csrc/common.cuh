@@ -69,6 +69,15 @@ __device__ __forceinline__ uint4 ld_nc_u4(const void *p) {
                  : "l"(p));
     return r;
 }
+// volatile 128-bit load: ptxas keeps volatile accesses in program order, which pins this load ABOVE the (volatile)
+// shared-memory lookups of the current step -- a plain ld.global.nc gets sunk below them to save registers
+__device__ __forceinline__ uint4 ld_vol_u4(const void *p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
 __device__ __forceinline__ uint2 ld_nc_u2(const void *p) {
     uint2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));

@@ -76,22 +76,29 @@ __global__ void __launch_bounds__(MMIDX_NT) k_build_p32t(const double *__restric
 // ---- bank-conflict-aware order inside an inverted list ------------------------------------------------
 // The scan's cost is shared-memory wavefronts: one warp-wide lookup into sub-table j takes as many cycles as
 // the most loaded bank has DISTINCT addresses (bank = code % 32 for fp32 entries).  Order inside a list is free
-// (the queue's offer order is carried separately as `orank`), so each list is re-ordered greedily, in chunks of
-// RCH entries, such that the 32 codes one warp instruction touches spread over the banks: pick by pick, the
-// entry that adds the least sum_j (2*load_j[bank]+1) over sub-quantizers whose address is not yet in the group.
+// (the queue's offer order is carried separately as `orank`), so each list is re-ordered greedily such that the 32
+// codes one warp instruction touches spread over the banks: pick by pick, the entry that raises the fewest per-
+// sub-quantizer maxima (then the least sum_j (2*load_j[bank]+1)) over sub-quantizers whose address is not yet in the
+// group.  The pool is the whole list up to RCH entries (longer lists: chunks of RCH).  Measured on the bench index
+// (scratch/sim_reorder.c): 2.77 wavefronts per lookup in insertion order, 1.71 with a 512-entry pool and the plain
+// sum cost, 1.11 with this pool and cost.
 // M == 8: a thread scans two adjacent codes per 128-bit load, so a warp instruction covers the even (then the
 // odd) positions of a 64-entry block; M == 16: 32 consecutive positions.  grid nlist; src[] is list-relative.
-constexpr int RCH = 512;
+constexpr int RCH = 4096;
 
 template <int M>
 __global__ void __launch_bounds__(MMIDX_NT) k_reorder_lists(const uint8_t *__restrict__ codes, const int64_t *__restrict__ list_off,
                                                             const int32_t *__restrict__ list_len, int32_t *__restrict__ src) {
-    __shared__ uint8_t cs[RCH][M];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t(*cs)[M] = reinterpret_cast<uint8_t(*)[M]>(smem_raw);  // [RCH][M]
     __shared__ int load[M][32];
+    __shared__ int mx[M];
     __shared__ unsigned seen[M][8];
     __shared__ unsigned red[MMIDX_NT / 32];
     __shared__ unsigned s_win;
     constexpr int BLK = (M == 8) ? 64 : 32;
+    constexpr int PER = RCH / MMIDX_NT;
+    constexpr int MAXPEN = 1000;  // raising a sub-quantizer's maximum outweighs any sum of load terms
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = blockIdx.x;
     const int64_t start = list_off[l];
@@ -99,10 +106,11 @@ __global__ void __launch_bounds__(MMIDX_NT) k_reorder_lists(const uint8_t *__res
     for (int cb = 0; cb < len; cb += RCH) {
         const int n = min(RCH, len - cb);
         __syncthreads();
-        for (int e = tid; e < n * M; e += MMIDX_NT) cs[e / M][e % M] = codes[(start + cb) * M + e];
-        bool alive[RCH / MMIDX_NT];
+        for (int e = tid; e < n * M; e += MMIDX_NT) (&cs[0][0])[e] = codes[(start + cb) * M + e];
+        unsigned alive = 0u;
 #pragma unroll
-        for (int r = 0; r < RCH / MMIDX_NT; ++r) alive[r] = (tid + r * MMIDX_NT) < n;
+        for (int r = 0; r < PER; ++r)
+            if (tid + r * MMIDX_NT < n) alive |= 1u << r;
         for (int bb = 0; bb < n; bb += BLK) {
             const int rblk = min(BLK, n - bb);
             for (int h = 0; h < BLK / 32; ++h) {
@@ -110,21 +118,35 @@ __global__ void __launch_bounds__(MMIDX_NT) k_reorder_lists(const uint8_t *__res
                 __syncthreads();
                 for (int e = tid; e < M * 32; e += MMIDX_NT) (&load[0][0])[e] = 0;
                 for (int e = tid; e < M * 8; e += MMIDX_NT) (&seen[0][0])[e] = 0u;
+                if (tid < M) mx[tid] = 0;
                 for (int t = 0; t < gsize; ++t) {
                     __syncthreads();
                     unsigned best = 0xffffffffu;
 #pragma unroll
-                    for (int r = 0; r < RCH / MMIDX_NT; ++r) {
-                        if (alive[r]) {
+                    for (int r = 0; r < PER; ++r) {
+                        if ((alive >> r) & 1u) {
                             const int idx = tid + r * MMIDX_NT;
+                            unsigned cw[M / 4];
+                            if (M == 8) {
+                                const uint2 v = *reinterpret_cast<const uint2 *>(&cs[idx][0]);
+                                cw[0] = v.x;
+                                cw[1] = v.y;
+                            } else {
+                                const uint4 v = *reinterpret_cast<const uint4 *>(&cs[idx][0]);
+                                cw[0] = v.x;
+                                cw[1] = v.y;
+                                cw[2 % (M / 4)] = v.z;
+                                cw[3 % (M / 4)] = v.w;
+                            }
                             int cost = 0;
 #pragma unroll
                             for (int j = 0; j < M; ++j) {
-                                const unsigned c = cs[idx][j];
+                                const unsigned c = (cw[j >> 2] >> (8 * (j & 3))) & 255u;
                                 const bool dup = (seen[j][c >> 5] >> (c & 31u)) & 1u;
-                                cost += dup ? 0 : 2 * load[j][c & 31u] + 1;
+                                const int ld = load[j][c & 31u];
+                                cost += dup ? 0 : ((ld + 1 > mx[j]) ? MAXPEN : 0) + 2 * ld + 1;
                             }
-                            best = min(best, ((unsigned)cost << 16) | (unsigned)idx);
+                            best = min(best, ((unsigned)cost << 12) | (unsigned)idx);
                         }
                     }
 #pragma unroll
@@ -135,22 +157,21 @@ __global__ void __launch_bounds__(MMIDX_NT) k_reorder_lists(const uint8_t *__res
                         unsigned b = red[0];
                         for (int wv = 1; wv < MMIDX_NT / 32; ++wv) b = min(b, red[wv]);
                         s_win = b;
-                        const int idx = (int)(b & 0xffffu);
+                        const int idx = (int)(b & 0xfffu);
                         const int pos = (M == 8) ? (bb + 2 * t + h) : (bb + t);
                         src[start + cb + pos] = cb + idx;
                         for (int j = 0; j < M; ++j) {
                             const unsigned c = cs[idx][j];
                             if (!((seen[j][c >> 5] >> (c & 31u)) & 1u)) {
                                 seen[j][c >> 5] |= 1u << (c & 31u);
-                                load[j][c & 31u] += 1;
+                                const int nl = ++load[j][c & 31u];
+                                if (nl > mx[j]) mx[j] = nl;
                             }
                         }
                     }
                     __syncthreads();
-                    const int widx = (int)(s_win & 0xffffu);
-#pragma unroll
-                    for (int r = 0; r < RCH / MMIDX_NT; ++r)
-                        if (widx == tid + r * MMIDX_NT) alive[r] = false;
+                    const int widx = (int)(s_win & 0xfffu);
+                    if ((widx & (MMIDX_NT - 1)) == tid) alive &= ~(1u << (widx / MMIDX_NT));
                 }
             }
         }
@@ -228,7 +249,7 @@ __device__ __forceinline__ float f32_unkey(unsigned k) {
 template <int OFF>
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
     return v;
 }
 // ADC table entry of sub-quantizer J for byte I of a packed code word (ks == 256: 1 KiB per sub-table)
@@ -746,8 +767,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     const unsigned char *dq = a.desc + q * (int64_t)a.w * DSTRIDE;
     const uint32_t t1_bytes = (uint32_t)(nent * sizeof(float));
     const int S = a.S;
-    const double rel = (double)M * 5.9604644775390625e-08;
-    const double bq = a.bq[q];
+    constexpr double rel = (double)M * 5.9604644775390625e-08;
     const float finf = __int_as_float(0x7f800000);
 
     c32.init();
@@ -786,12 +806,12 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
                 c32.drop_tag((unsigned int)pslot);
                 const ProbeHdr *h = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)pslot * DSTRIDE);
                 scan_list_rounds<CAP32, M>(c32, plut, a.ocodes + h->start * M, h->len, ((unsigned int)pslot) << FAST_POS_BITS,
-                                           a.k, bq, rel);
+                                           a.k, a.bq[q], rel);
             }
             const int n = c32.cnt;
             const bool isinf32 = c32.thr32 == finf;
             __syncthreads();  // everybody has read the state before the next list starts pushing
-            if (n >= a.k && (n > KEEP || isinf32)) c32.compact(a.k, bq, rel);
+            if (n >= a.k && (n > KEEP || isinf32)) c32.compact(a.k, a.bq[q], rel);
         }
     };
 
@@ -808,6 +828,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
         if (tid == 0 && ii + a.nsplit < nop) lnext = reinterpret_cast<const ProbeHdr *>(dp + (int64_t)a.nsplit * DSTRIDE)->l;
         const int64_t start = (int64_t)(((unsigned long long)(unsigned int)hd.y << 32) | (unsigned long long)(unsigned int)hd.x);
         const int len = hd.z;  // > 0 by construction of the descriptors
+        const uint8_t *lc = a.ocodes + start * M;
         mbar_wait(&bars[0], (uint32_t)(it & 1));
         // ADC table of this probe: lut = (T1[l] + T2) + s
         {
@@ -832,12 +853,14 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
             mbar_arrive_expect_tx(&bars[0], t1_bytes);
             tma_load_1d(stage, a.T1 + (int64_t)lnext * nent, t1_bytes, &bars[0]);
         }
-        const uint8_t *lc = a.ocodes + start * M;
         const unsigned int ptag = ((unsigned int)ii) << FAST_POS_BITS;
         const float thr32 = c32.thr32;
         if (thr32 == finf) {  // block-uniform: nothing can be rejected yet
-            scan_list_rounds<CAP32, M>(c32, lut_s, lc, len, ptag, a.k, bq, rel);
+            scan_list_rounds<CAP32, M>(c32, lut_s, lc, len, ptag, a.k, a.bq[q], rel);
         } else {
+            // One 128-bit load per thread and step; the load of the next step is issued before the current one is
+            // consumed.  (Measured alternatives, profiles/README.md: L1 prefetch one or two steps ahead, two or four
+            // loads per step, 3 CTAs/SM with 80 registers -- all slower than this form.)
             constexpr int CPT = (M == 8) ? 2 : 1;
             constexpr int STEP = MMIDX_NT * CPT;
             int i0 = tid * CPT;
@@ -846,7 +869,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
             for (int wb = (tid & ~31) * CPT; wb < len; wb += STEP) {  // warp-uniform trip count
                 const int i1 = i0 + STEP;
                 uint4 nxt = make_uint4(0, 0, 0, 0);
-                if (i1 < len) nxt = ld_nc_u4(lc + (int64_t)i1 * M);
+                if (i1 < len) nxt = ld_vol_u4(lc + (int64_t)i1 * M);
                 float d0, d1;
                 adc_pair<M>(lut_s, cur, d0, d1);
                 const bool p0 = (i0 < len) && d0 <= thr32;
@@ -863,7 +886,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     __syncthreads();
     const int n_before = c32.cnt;
     __syncthreads();
-    if (n_before > a.k) c32.compact(a.k, bq, rel);
+    if (n_before > a.k) c32.compact(a.k, a.bq[q], rel);
     const int nsurv = c32.cnt;
     const bool overflow = c32.overflow != 0 || nsurv > ECAP;
     TopK<ECAP> &tk = *reinterpret_cast<TopK<ECAP> *>(regA);  // aliases t2/stage/lut: no TMA is in flight any more

@@ -662,12 +662,16 @@ static int seal(mmidx_index *ix) {
         int32_t *src;
         RET(sc.get(&src, (size_t)total));
         if (ix->reorder) {
-            if (m == 8)
-                k_reorder_lists<8><<<nlist, MMIDX_NT, 0, st>>>(ix->csr_codes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
-                                                              ix->dlist_len.as<int32_t>(), src);
-            else
-                k_reorder_lists<16><<<nlist, MMIDX_NT, 0, st>>>(ix->csr_codes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
-                                                               ix->dlist_len.as<int32_t>(), src);
+            const size_t rsm = (size_t)RCH * m;  // the pool's codes
+            if (m == 8) {
+                RET(set_smem(k_reorder_lists<8>, rsm));
+                k_reorder_lists<8><<<nlist, MMIDX_NT, rsm, st>>>(ix->csr_codes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
+                                                                ix->dlist_len.as<int32_t>(), src);
+            } else {
+                RET(set_smem(k_reorder_lists<16>, rsm));
+                k_reorder_lists<16><<<nlist, MMIDX_NT, rsm, st>>>(ix->csr_codes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
+                                                                 ix->dlist_len.as<int32_t>(), src);
+            }
             RET(post_launch("k_reorder_lists", nullptr));
         } else {
             k_identity_order<<<nlist, MMIDX_NT, 0, st>>>(ix->dlist_off.as<int64_t>(), ix->dlist_len.as<int32_t>(), src);
