@@ -162,10 +162,9 @@ struct TopkOut {
     int nparts;
 };
 
+// writes the first n (<= k) entries of a collector that is already in output order (finalize() / sort_first())
 template <int CAP>
-__device__ void write_result(TopK<CAP> &tk, const TopkOut &o, int64_t q, int part, int k, double extra_tie) {
-    bool amb;
-    const int n = tk.finalize(k, &amb);
+__device__ void write_sorted(TopK<CAP> &tk, const TopkOut &o, int64_t q, int part, int k, int n, bool amb) {
     const int64_t base = (q * o.nparts + part) * (int64_t)k;
     for (int i = threadIdx.x; i < k; i += MMIDX_NT) {
         bool v = i < n;
@@ -175,14 +174,21 @@ __device__ void write_result(TopK<CAP> &tk, const TopkOut &o, int64_t q, int par
     }
     if (threadIdx.x == 0) {
         o.cnt[q * o.nparts + part] = n;
-        // a partial result that discarded ties at distance t makes the final answer ambiguous iff t == final T
-        if (n == k && extra_tie == tk.dist[n - 1]) amb = true;
         if (o.tie) o.tie[q * o.nparts + part] = (n == k && amb) ? tk.dist[n - 1] : -1.0;
         if (o.amb_list && amb) {
             int slot = atomicAdd(o.amb_count, 1);
             o.amb_list[slot] = (int32_t)q;
         }
     }
+}
+
+template <int CAP>
+__device__ void write_result(TopK<CAP> &tk, const TopkOut &o, int64_t q, int part, int k, double extra_tie) {
+    bool amb;
+    const int n = tk.finalize(k, &amb);
+    // a partial result that discarded ties at distance t makes the final answer ambiguous iff t == final T
+    if (n == k && extra_tie == tk.dist[n - 1]) amb = true;
+    write_sorted(tk, o, q, part, k, n, amb);
 }
 
 // K1b: top-w entries of each row of D in queue order. grid nq.

@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "tie_resolve.cuh"
+#include "coarse_fast.cuh"
 #include "fast_scan.cuh"
 
 using namespace mmidx;
@@ -151,11 +152,15 @@ struct mmidx_index {
     std::vector<int32_t> h_list_len;
     std::vector<int64_t> h_list_off;
     cudaStream_t stream = nullptr;
+    // mmidx_search: copies overlap the kernels of other chunks; chunks alternate between `stream` and `comp2_stream`
+    // so that the tail of one chunk's scan overlaps the next chunk's kernels
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, comp2_stream = nullptr;
     std::mutex mu;
     StageTimer timer;
     int last_launches = 0;
     // fast path tables (fast_scan.cuh), rebuilt when a quantizer or the permutation changes
     DevBuf dT1, dP32t, dt1max, dpmax, dstats;
+    DevBuf dC32, dc2, dcmax;  // coarse_fast.cuh: fp32 copy of the coarse quantizer, ||C||^2, max ||C||
     std::vector<int32_t> shard_map;  // optional list -> owning shard (default l % shard_count)
     bool fast_ready = false;
     bool fast_len_ok = true;   // every list shorter than 2^22 entries (packed payload of the fp32 collector)
@@ -281,6 +286,9 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
         if (ix->stream) {
             cudaStreamSynchronize(ix->stream);
             cudaStreamDestroy(ix->stream);
+            if (ix->h2d_stream) cudaStreamDestroy(ix->h2d_stream);
+            if (ix->d2h_stream) cudaStreamDestroy(ix->d2h_stream);
+            if (ix->comp2_stream) cudaStreamDestroy(ix->comp2_stream);
         }
     }
     DeviceGuard g(ix->device);
@@ -327,6 +335,14 @@ extern "C" int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C) {
     k_transpose<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->stream>>>(ix->dC.as<double>(), ix->p.nlist, ix->p.d,
                                                                       ix->dCt.as<double>());
     RET(post_launch("k_transpose", nullptr));
+    // fp32 filter tables of the coarse stage (coarse_fast.cuh)
+    RET(ix->dC32.reserve(cnt * sizeof(float), 0, ix->stream));
+    RET(ix->dc2.reserve((size_t)ix->p.nlist * sizeof(float), 0, ix->stream));
+    RET(ix->dcmax.reserve(sizeof(float), 0, ix->stream));
+    CK(cudaMemsetAsync(ix->dcmax.p, 0, sizeof(float), ix->stream));
+    k_coarse_tables<<<ix->p.nlist, MMIDX_NT, 0, ix->stream>>>(ix->dC.as<double>(), ix->p.d, ix->dC32.as<float>(),
+                                                             ix->dc2.as<float>(), ix->dcmax.as<float>());
+    RET(post_launch("k_coarse_tables", nullptr));
     CK(cudaStreamSynchronize(ix->stream));
     ix->has_C = true;
     ix->fast_ready = false;
@@ -724,17 +740,13 @@ struct StageMark {
 static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w, int32_t *dprobes, Scratch &sc,
                             cudaStream_t st, int *launches) {
     const int nlist = ix->p.nlist, d = ix->p.d;
-    double *D, *pd;
+    double *pd;
     int32_t *pcnt, *amb_list, *amb_count;
-    RET(sc.get(&D, (size_t)nq * nlist));
     RET(sc.get(&pd, (size_t)nq * w));
     RET(sc.get(&pcnt, (size_t)nq));
     RET(sc.get(&amb_list, (size_t)nq));
     RET(sc.get(&amb_count, 1));
     CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
-    dim3 g1((unsigned)((nlist + MMIDX_NT - 1) / MMIDX_NT), (unsigned)((nq + QT - 1) / QT));
-    k_sqdist_matrix<<<g1, MMIDX_NT, 0, st>>>(dQ, ix->dCt.as<double>(), nq, nlist, d, D);
-    RET(post_launch("k_sqdist_matrix", launches));
     TopkOut o{};
     o.iids = dprobes;
     o.dist = pd;
@@ -744,25 +756,55 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     o.amb_list = amb_list;
     o.amb_count = amb_count;
     o.nparts = 1;
-    if (cap_for(w) == 1024) {
-        size_t smem = topk_bytes<1024>();
-        RET(set_smem(k_select_rows<1024>, smem));
-        k_select_rows<1024><<<(unsigned)nq, MMIDX_NT, smem, st>>>(D, nlist, w, o);
-    } else {
-        size_t smem = topk_bytes<2048>();
-        RET(set_smem(k_select_rows<2048>, smem));
-        k_select_rows<2048><<<(unsigned)nq, MMIDX_NT, smem, st>>>(D, nlist, w, o);
-    }
-    RET(post_launch("k_select_rows", launches));
-    // ordered tie pass for rows whose w-th boundary was an exact tie
+    const size_t tkb = cap_for(w) == 1024 ? topk_bytes<1024>() : topk_bytes<2048>();
+    // survivors evaluated per batch: up to 16 rows of squared terms, at most 32 KB (at least one row)
+    const int vb = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)32 << 10) / ((size_t)(d + 1) * 8)));
+    const size_t vsm = tkb + (size_t)d * 8 + (((size_t)nlist * 4 + 7) & ~(size_t)7) + (size_t)cap_for(w) * 4 + (size_t)vb * (d + 1) * 8;
+    const bool fastc = !ix->force_exact && vsm <= 160 * 1024;
     TieLists tl;
     RET(sc.get(&tl.seq, (size_t)nq * w));
     RET(sc.get(&tl.pay, (size_t)nq * w));
     RET(sc.get(&tl.eq, (size_t)nq * w));
     RET(sc.get(&tl.cnt, (size_t)nq));
     const int tg = (int)std::min<int64_t>(nq, 296);
-    k_tie_collect_rows<<<tg, MMIDX_NT, 0, st>>>(D, nlist, w, pd, amb_list, amb_count, tl);
-    RET(post_launch("k_tie_collect_rows", launches));
+    if (fastc) {
+        // fp32 filter (tiled FFMA GEMM) + exact binary64 verification of the few centroids inside the error band
+        float *A32;
+        RET(sc.get(&A32, (size_t)nq * nlist));
+        dim3 gg((unsigned)((nlist + CG_BN - 1) / CG_BN), (unsigned)((nq + CG_BM - 1) / CG_BM));
+        k_coarse_f32<<<gg, MMIDX_NT, 0, st>>>(dQ, ix->dC32.as<float>(), ix->dc2.as<float>(), nq, nlist, d, A32);
+        RET(post_launch("k_coarse_f32", launches));
+        if (cap_for(w) == 1024) {
+            RET(set_smem(k_coarse_verify<1024>, vsm));
+            k_coarse_verify<1024><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, o);
+        } else {
+            RET(set_smem(k_coarse_verify<2048>, vsm));
+            k_coarse_verify<2048><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, o);
+        }
+        RET(post_launch("k_coarse_verify", launches));
+        // only rows ranked by the kernel's exact sweep (band wider than the collector) can be flagged here
+        k_tie_collect_rows_direct<<<tg, MMIDX_NT, 0, st>>>(dQ, ix->dC.as<double>(), nlist, d, w, pd, amb_list, amb_count, tl);
+        RET(post_launch("k_tie_collect_rows_direct", launches));
+    } else {
+        double *D;
+        RET(sc.get(&D, (size_t)nq * nlist));
+        dim3 g1((unsigned)((nlist + MMIDX_NT - 1) / MMIDX_NT), (unsigned)((nq + QT - 1) / QT));
+        k_sqdist_matrix<<<g1, MMIDX_NT, 0, st>>>(dQ, ix->dCt.as<double>(), nq, nlist, d, D);
+        RET(post_launch("k_sqdist_matrix", launches));
+        if (cap_for(w) == 1024) {
+            size_t smem = topk_bytes<1024>();
+            RET(set_smem(k_select_rows<1024>, smem));
+            k_select_rows<1024><<<(unsigned)nq, MMIDX_NT, smem, st>>>(D, nlist, w, o);
+        } else {
+            size_t smem = topk_bytes<2048>();
+            RET(set_smem(k_select_rows<2048>, smem));
+            k_select_rows<2048><<<(unsigned)nq, MMIDX_NT, smem, st>>>(D, nlist, w, o);
+        }
+        RET(post_launch("k_select_rows", launches));
+        // ordered tie pass for rows whose w-th boundary was an exact tie
+        k_tie_collect_rows<<<tg, MMIDX_NT, 0, st>>>(D, nlist, w, pd, amb_list, amb_count, tl);
+        RET(post_launch("k_tie_collect_rows", launches));
+    }
     size_t fs = (size_t)w * 16;
     RET(set_smem(k_tie_finish, std::max<size_t>(fs, 1024 * 16)));
     k_tie_finish<<<tg, MMIDX_NT, fs, st>>>(1, nq, w, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, dprobes, pd, nullptr);
@@ -1540,12 +1582,64 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
     RET(sc.get(&ddist, (size_t)nq * k));
     RET(sc.get(&diids, (size_t)nq * k));
     RET(sc.get(&dcnt, (size_t)nq));
-    CK(cudaMemcpyAsync(dQ, Q, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
-    RET(search_dev_impl(ix, nq, dQ, k, diids, ddist, nullptr, nullptr, dcnt, st, false));
-    CK(cudaMemcpyAsync(out_iids, diids, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out_dist, ddist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-    if (out_count) CK(cudaMemcpyAsync(out_count, dcnt, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    // Query chunks are pipelined over three streams: the host->device copy of chunk c+1 and the device->host copy of
+    // chunk c-1 run under the kernels of chunk c (pinned host buffers; pageable ones still work, just serialised).
+    const int64_t CH = 2048;
+    if (nq <= 2 * CH) {
+        CK(cudaMemcpyAsync(dQ, Q, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
+        RET(search_dev_impl(ix, nq, dQ, k, diids, ddist, nullptr, nullptr, dcnt, st, false));
+        CK(cudaMemcpyAsync(out_iids, diids, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_dist, ddist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+        if (out_count) CK(cudaMemcpyAsync(out_count, dcnt, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return MMIDX_OK;
+    }
+    if (!ix->h2d_stream) {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        if (!ix->h2d_stream) {
+            CK(cudaStreamCreateWithFlags(&ix->h2d_stream, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&ix->d2h_stream, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&ix->comp2_stream, cudaStreamNonBlocking));
+        }
+    }
+    cudaStream_t sh = ix->h2d_stream, sd = ix->d2h_stream, sc2 = ix->comp2_stream;
+    const int nch = (int)((nq + CH - 1) / CH);
+    std::vector<cudaEvent_t> ev((size_t)2 * nch + 1, nullptr);
+    int rc = MMIDX_OK;
+    auto mk = [&](cudaEvent_t &e, cudaStream_t s_) {
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, s_) != cudaSuccess)
+            rc = fail(MMIDX_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
+    };
+    mk(ev[2 * nch], st);  // the scratch buffers exist (stream-ordered allocation on st)
+    if (rc == MMIDX_OK && cudaStreamWaitEvent(sh, ev[2 * nch], 0) != cudaSuccess) rc = fail(MMIDX_ERR_CUDA, "cudaStreamWaitEvent");
+    if (rc == MMIDX_OK && cudaStreamWaitEvent(sd, ev[2 * nch], 0) != cudaSuccess) rc = fail(MMIDX_ERR_CUDA, "cudaStreamWaitEvent");
+    if (rc == MMIDX_OK && cudaStreamWaitEvent(sc2, ev[2 * nch], 0) != cudaSuccess) rc = fail(MMIDX_ERR_CUDA, "cudaStreamWaitEvent");
+    for (int c = 0; c < nch && rc == MMIDX_OK; ++c) {
+        const int64_t q0 = (int64_t)c * CH, nb = std::min(CH, nq - q0);
+        if (cudaMemcpyAsync(dQ + q0 * ix->p.d, Q + q0 * ix->p.d, sizeof(double) * (size_t)nb * ix->p.d, cudaMemcpyHostToDevice, sh) != cudaSuccess) {
+            rc = fail(MMIDX_ERR_CUDA, "cudaMemcpyAsync H2D");
+            break;
+        }
+        mk(ev[2 * c], sh);
+        if (rc != MMIDX_OK) break;
+        cudaStream_t cs = (c & 1) ? sc2 : st;
+        cudaStreamWaitEvent(cs, ev[2 * c], 0);
+        rc = search_dev_impl(ix, nb, dQ + q0 * ix->p.d, k, diids + q0 * k, ddist + q0 * k, nullptr, nullptr, dcnt + q0, cs, false);
+        if (rc != MMIDX_OK) break;
+        mk(ev[2 * c + 1], cs);
+        if (rc != MMIDX_OK) break;
+        cudaStreamWaitEvent(sd, ev[2 * c + 1], 0);
+        cudaMemcpyAsync(out_iids + q0 * k, diids + q0 * k, sizeof(int32_t) * (size_t)nb * k, cudaMemcpyDeviceToHost, sd);
+        cudaMemcpyAsync(out_dist + q0 * k, ddist + q0 * k, sizeof(double) * (size_t)nb * k, cudaMemcpyDeviceToHost, sd);
+        if (out_count) cudaMemcpyAsync(out_count + q0, dcnt + q0, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, sd);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(sh), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(sd);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(sc2);
+    for (cudaEvent_t e : ev)
+        if (e) cudaEventDestroy(e);
+    if (rc != MMIDX_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(MMIDX_ERR_CUDA, "mmidx_search: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return MMIDX_OK;
 }
 

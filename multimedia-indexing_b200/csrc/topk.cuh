@@ -193,16 +193,53 @@ struct TopK {
         if (__syncthreads_or(*(volatile int *)&cnt > CAP - ROUND)) compact(k, KEEP_MAX);
     }
 
-    // reduce to the final <=k entries, sorted in BoundedPriorityQueue iteration order
-    // (ascending distance; among equal distances the later-offered, i.e. larger seq, first).
-    // Returns the number of results; *ambiguous is set when an exact tie at the k-th boundary was cut.
-    __device__ int finalize(int k, bool *ambiguous) {
+    // Replays the queue's tie rule when the first n entries are a COMPLETE candidate set, i.e. they contain every
+    // candidate whose distance is <= T, the k-th smallest (n > k).  BoundedPriorityQueue keeps, among the entries with
+    // dist <= T, the first k in offer order (set A); of the entries of A tied at T only the `need` latest-offered
+    // survive, and tied entries offered after A were rejected on arrival.  Losers get dist = +inf and
+    // drop out in finalize().  flag: scratch for n ints.  All threads; block-uniform.
+    __device__ void kill_tie_losers(int n, int k, int *flag) {
         const int tid = threadIdx.x;
         __syncthreads();
-        if (cnt > k) compact(k, k);
-        const int n = cnt;
+        unsigned long long kth;
+        int need, neq;
+        select_kth(n, k, kth, need, neq);
+        if (neq > need) {  // block-uniform
+            const double T = __longlong_as_double((long long)kth);
+            // rank among the le-entries by offer sequence; A = the first k of them
+            for (int i = tid; i < n; i += MMIDX_NT) {
+                int f = 0;
+                if (dist[i] <= T) {
+                    int rank = 0;
+                    const unsigned long long si = seq[i];
+                    for (int j = 0; j < n; ++j) rank += (dist[j] <= T && seq[j] < si) ? 1 : 0;
+                    f = (rank < k) ? ((dist[i] == T) ? 2 : 1) : 3;  // 2: tied entry inside A, 3: offered after A
+                }
+                flag[i] = f;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += MMIDX_NT) {
+                const int f = flag[i];
+                bool kill = (f == 3 && dist[i] == T);
+                if (f == 2) {
+                    int later = 0;  // tied entries of A offered after this one
+                    const unsigned long long si = seq[i];
+                    for (int j = 0; j < n; ++j) later += (flag[j] == 2 && seq[j] > si) ? 1 : 0;
+                    kill = later >= need;  // only the `need` latest-offered tied entries stay
+                }
+                if (kill) dist[i] = __longlong_as_double(0x7ff0000000000000LL);
+            }
+            __syncthreads();
+        }
+    }
+
+    // sorts the first n entries (n <= CAP) in BoundedPriorityQueue iteration order: ascending distance, among equal
+    // distances the later-offered (larger seq) first.  Entries [n, next power of two) are overwritten with padding.
+    __device__ void sort_first(int n) {
+        const int tid = threadIdx.x;
         int n2 = 1;
         while (n2 < n) n2 <<= 1;
+        __syncthreads();
         for (int i = n + tid; i < n2; i += MMIDX_NT) {
             dist[i] = __longlong_as_double(0x7ff0000000000000LL);
             seq[i] = 0ull;
@@ -231,6 +268,16 @@ struct TopK {
             }
         }
         __syncthreads();
+    }
+
+    // reduce to the final <=k entries, sorted in BoundedPriorityQueue iteration order
+    // (ascending distance; among equal distances the later-offered, i.e. larger seq, first).
+    // Returns the number of results; *ambiguous is set when an exact tie at the k-th boundary was cut.
+    __device__ int finalize(int k, bool *ambiguous) {
+        __syncthreads();
+        if (cnt > k) compact(k, k);
+        const int n = cnt;
+        sort_first(n);
         *ambiguous = (n == k) && (tie_drop == dist[n - 1]);
         return n;
     }

@@ -175,6 +175,35 @@ def test_ties_at_the_kth_boundary_follow_the_queue_rules():
     assert (ix2.computeNearestCoarseIndices(Q) == O.coarse_topw(Cd, Q, 3)).all()
 
 
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_coarse_probes_vs_oracle(mode, monkeypatch):
+    """computeNearestCoarseIndices (IVFPQ.java:575-601): fp32 filter + exact verification == the exact kernels == oracle,
+    including duplicated centroids (exact ties at and across the w-th boundary) and a tie class larger than the
+    verification collector (the kernel's exact sweep + ordered tie pass)."""
+    if mode == "exact":
+        monkeypatch.setenv("MMIDX_MODE", "exact")
+    rng = np.random.default_rng(11)
+    d, m, ks = 24, 4, 16
+    P = rng.normal(0, 10, size=(m, ks, d // m))
+    # (a) generic real-valued centroids and queries, w from 1 to nlist
+    Cq = rng.normal(60, 25, size=(300, d))
+    Q = rng.normal(60, 25, size=(40, d))
+    for w in (1, 7, 32, 300):
+        ix = make_ivfpq(d, m, ks, 300, w, Cq, P)
+        assert (ix.computeNearestCoarseIndices(Q) == O.coarse_topw(Cq, Q, w)).all(), f"w={w}"
+    # (b) every centroid repeated 5 times: ties everywhere, cut at the boundary for w not a multiple of 5
+    Cd = np.repeat(np.rint(rng.normal(60, 25, size=(60, d))), 5, axis=0)[rng.permutation(300)]
+    Qi = np.rint(rng.normal(60, 25, size=(25, d)))
+    for w in (3, 16, 64):
+        ix = make_ivfpq(d, m, ks, 300, w, Cd, P)
+        assert (ix.computeNearestCoarseIndices(Qi) == O.coarse_topw(Cd, Qi, w)).all(), f"dup w={w}"
+    # (c) 1500 identical centroids among 1600: the tie class exceeds the 1024-entry collector
+    Cb = np.vstack([np.tile(Cq[:1], (1500, 1)), Cq[1:101]])[rng.permutation(1600)]
+    ix = make_ivfpq(d, m, ks, 1600, 40, Cb, P)
+    Qb = np.vstack([Cq[:1] + 0.5, Q[:7]])
+    assert (ix.computeNearestCoarseIndices(Qb) == O.coarse_topw(Cb, Qb, 40)).all(), "wide tie class"
+
+
 def test_bulk_reload_matches_incremental_index():
     """indexPQCode / loadIndexInMemory path (IVFPQ.java:357-386, 680-728)."""
     d, m, ks, nlist, w, k = 32, 4, 64, 16, 4, 10
