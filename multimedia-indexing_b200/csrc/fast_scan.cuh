@@ -485,9 +485,11 @@ __device__ __forceinline__ double exact_adc(const double *__restrict__ Cl, const
     return dist;
 }
 
-template <int CAP32>
+// exact collector for the survivors (more survivors than this -> direct kernel); their codes are staged in the dead
+// fp32 key array of the first collector, which bounds it at 4 * CAP32 / M
+template <int CAP32, int M>
 struct FastExactCap {
-    static constexpr int value = 512;  // exact collector for the survivors; more survivors than this -> direct kernel
+    static constexpr int value = (4 * CAP32 / M) < 512 ? (4 * CAP32 / M) : 512;
 };
 
 
@@ -739,7 +741,7 @@ __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t
 // the next T1 row, then a barrier-free sweep over the list with the next 128-bit code load in flight.
 template <int CAP32, int M>
 __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
-    constexpr int ECAP = FastExactCap<CAP32>::value;
+    constexpr int ECAP = FastExactCap<CAP32, M>::value;
     constexpr int ks = 256;  // the fused kernel is specialised for full byte codes (host checks ks == 256)
     constexpr int nent = M * ks;
     constexpr int NV = nent / (4 * MMIDX_NT);  // float4 entries of one table per thread
