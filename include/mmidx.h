@@ -150,6 +150,10 @@ int mmidx_last_timings(mmidx_t *ix, float *out5);
 int mmidx_enable_timings(mmidx_t *ix, int32_t on);
 /* number of kernels the most recent call launched */
 int mmidx_last_launches(mmidx_t *ix, int32_t *out);
+/* debug counters of the fused IVFPQ scan kernel, accumulated since mmidx_create when MMIDX_STATS=1 was set (else
+ * MMIDX_ERR_STATE): [0]=candidates scanned [1]=lists re-scanned after a collector overflow of the barrier-free sweep
+ * [2]=survivors evaluated in binary64 [3]=queries handed to the table-free exact kernel. Host-syncs. */
+int mmidx_debug_stats(mmidx_t *ix, uint64_t *out4);
 
 /* ---- VLAD: VladAggregator.aggregateInternal VladAggregator.java:56-70 over
  * AbstractFeatureAggregator.computeNearestCentroid AFA.java:136-155, batched over images.

@@ -71,6 +71,7 @@ _SIGS = {
     "mmidx_last_timings": [_vp, _vp],
     "mmidx_enable_timings": [_vp, _i32],
     "mmidx_last_launches": [_vp, C.POINTER(_i32)],
+    "mmidx_debug_stats": [_vp, _vp],
     "mmidx_vlad": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32],
     "mmidx_vlad_dev": [_vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
 }

@@ -233,7 +233,7 @@ struct FastArgs {
     int resolve_ties;           // 1: replay the queue's tie rule inside the kernel (unsharded, nsplit == 1)
     int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
     int32_t *fb_count;
-    unsigned long long *stats;  // optional [4]: candidates, collector pushes, exact evaluations, overflows
+    unsigned long long *stats;  // optional [4]: candidates, re-scanned lists, exact evaluations, direct fallbacks
 };
 
 // order-preserving map of fp32 bit patterns to unsigned keys (d32 may be slightly negative)
@@ -807,6 +807,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
             const int ov = c32.ovf;
             __syncthreads();
             if (ov) {  // block-uniform
+                if (a.stats && tid == 0) atomicAdd(&a.stats[1], 1ull);
                 c32.drop_tag((unsigned int)pslot);
                 const ProbeHdr *h = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)pslot * DSTRIDE);
                 scan_list_rounds<CAP32, M>(c32, plut, a.ocodes + h->start * M, h->len, ((unsigned int)pslot) << FAST_POS_BITS,

@@ -281,7 +281,7 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
             unsigned long long h[4] = {0, 0, 0, 0};
             cudaDeviceSynchronize();
             cudaMemcpy(h, ix->dstats.p, sizeof(h), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[mmidx stats] candidates=%llu filter_passes=%llu exact_accepts=%llu\n", h[0], h[1], h[2]);
+            fprintf(stderr, "[mmidx stats] candidates=%llu rescanned_lists=%llu survivors=%llu direct_fallbacks=%llu\n", h[0], h[1], h[2], h[3]);
         }
         if (ix->stream) {
             cudaStreamSynchronize(ix->stream);
@@ -756,10 +756,13 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     o.amb_list = amb_list;
     o.amb_count = amb_count;
     o.nparts = 1;
-    const size_t tkb = cap_for(w) == 1024 ? topk_bytes<1024>() : topk_bytes<2048>();
+    // verification collector: the survivors are w plus the few centroids inside the error band; a small collector keeps
+    // the CTA's shared memory low (8 CTAs/SM at w <= 128).  More survivors than ccap -> the kernel's exact sweep.
+    const int ccap = w <= 128 ? 256 : cap_for(w);
+    const size_t tkb = ccap == 256 ? topk_bytes<256>() : (ccap == 1024 ? topk_bytes<1024>() : topk_bytes<2048>());
     // survivors evaluated per batch: up to 16 rows of squared terms, at most 32 KB (at least one row)
     const int vb = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)32 << 10) / ((size_t)(d + 1) * 8)));
-    const size_t vsm = tkb + (size_t)d * 8 + (((size_t)nlist * 4 + 7) & ~(size_t)7) + (size_t)cap_for(w) * 4 + (size_t)vb * (d + 1) * 8;
+    const size_t vsm = tkb + (size_t)d * 8 + (((size_t)nlist * 4 + 7) & ~(size_t)7) + (size_t)ccap * 4 + (size_t)vb * (d + 1) * 8;
     const bool fastc = !ix->force_exact && vsm <= 160 * 1024;
     TieLists tl;
     RET(sc.get(&tl.seq, (size_t)nq * w));
@@ -774,7 +777,10 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
         dim3 gg((unsigned)((nlist + CG_BN - 1) / CG_BN), (unsigned)((nq + CG_BM - 1) / CG_BM));
         k_coarse_f32<<<gg, MMIDX_NT, 0, st>>>(dQ, ix->dC32.as<float>(), ix->dc2.as<float>(), nq, nlist, d, A32);
         RET(post_launch("k_coarse_f32", launches));
-        if (cap_for(w) == 1024) {
+        if (ccap == 256) {
+            RET(set_smem(k_coarse_verify<256>, vsm));
+            k_coarse_verify<256><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, o);
+        } else if (ccap == 1024) {
             RET(set_smem(k_coarse_verify<1024>, vsm));
             k_coarse_verify<1024><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, o);
         } else {
@@ -1784,6 +1790,15 @@ extern "C" int mmidx_last_timings(mmidx_t *ix, float *out5) {
         CK(cudaEventElapsedTime(&ms, s.a, s.b));
         out5[s.stage] += ms;
     }
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_debug_stats(mmidx_t *ix, uint64_t *out4) {
+    if (!ix || !out4) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (!ix->want_stats || !ix->dstats.p) return fail(MMIDX_ERR_STATE, "MMIDX_STATS=1 was not set or no fast search ran yet");
+    DeviceGuard g(ix->device);
+    CK(cudaStreamSynchronize(ix->stream));
+    CK(cudaMemcpy(out4, ix->dstats.p, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost));
     return MMIDX_OK;
 }
 

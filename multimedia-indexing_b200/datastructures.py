@@ -224,6 +224,12 @@ class AbstractSearchStructure:
         check(lib.mmidx_last_launches(self._h, C.byref(n)))
         return n.value
 
+    def debugStats(self):
+        """MMIDX_STATS=1 counters of the fused scan kernel: candidates, re-scanned lists, survivors, direct fallbacks"""
+        out = np.zeros(4, dtype=np.uint64)
+        check(lib.mmidx_debug_stats(self._h, _ptr(out)))
+        return out
+
     def scanBytes(self, Q):
         Q = _f64(Q)
         out = C.c_int64()

@@ -362,3 +362,53 @@ def test_fast_path_overflow_falls_back_to_direct_kernel():
     assert_same(ix.searchBatch(k, Q), ref, "overflow -> direct")
     big = np.vstack([Q] * 60)  # > 592 queries: one CTA per query
     assert_same(ix.searchBatch(k, big), tuple(np.concatenate([r] * 60) for r in ref), "overflow -> direct, nsplit=1")
+
+
+def test_barrier_free_sweep_overflow_is_rolled_back(monkeypatch):
+    """Adversarial offer order for the fused scan kernel: the nearest list holds only far candidates (the admission
+    threshold it leaves is loose), the next lists hold thousands of candidates that all beat it, so the barrier-free
+    sweep runs past the fp32 collector; its entries must be dropped and the list scanned again with round barriers.
+    Lists are crafted through the bulk-reload entry point (indexPQCode, IVFPQ.java:357-386)."""
+    monkeypatch.setenv("MMIDX_STATS", "1")
+    rng = np.random.default_rng(5)
+    d, m, ks, nlist, w, k = 64, 8, 256, 4, 4, 20
+    S = d // m
+    P = rng.normal(0, 5, size=(m, ks, S))
+    Cq = np.zeros((nlist, d))
+    Cq[:, 0] = [0.0, 6.0, 12.0, 18.0]  # a query near the origin ranks the lists 0, 1, 2, 3
+    Q = rng.normal(0, 0.3, size=(6, d))
+    Q = np.vstack([Q] * 120)            # > 592 queries: one CTA per query
+    q0 = Q[0]
+
+    def pick(l, nearest, count, width):
+        r = (Cq[l] - q0).reshape(m, S)
+        lut = ((r[:, None, :] - P) ** 2).sum(-1)                       # [m][ks]
+        order = np.argsort(lut, axis=1)
+        pool = order[:, :width] if nearest else order[:, -width:]
+        return np.stack([pool[j, rng.integers(0, width, size=count)] for j in range(m)], axis=1).astype(np.uint8)
+
+    codes = np.vstack([pick(0, False, 150, 16), pick(1, True, 5000, 6), pick(2, True, 3000, 6), pick(3, False, 40, 16)])
+    lists = np.concatenate([np.full(150, 0), np.full(5000, 1), np.full(3000, 2), np.full(40, 3)]).astype(np.int32)
+    sh = rng.permutation(len(lists))
+    lists, codes = lists[sh], codes[sh]
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    ix.indexPQCodes(None, lists, codes)
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    ref = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=O.num_threads())
+    assert_same(ix.searchBatch(k, Q), ref, "sweep overflow")
+    st = ix.debugStats()
+    assert st[1] >= len(Q) and st[3] == 0, f"the re-scan path did not run (stats {st})"
+    assert np.isin(lists[ref[0][0]], [1, 2]).all()  # the scenario is what it claims: the winners sit in the later lists
+
+
+def test_config4_geometry_large_batch():
+    """m = 16, S = 8 (BASELINE configs[3] geometry, scaled down) with one CTA per query."""
+    d, m, ks, nlist, w, n, nq, k = 128, 16, 256, 128, 32, 40000, 1200, 100
+    ce = synth.mixture_centers(d, 256)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=10000, iters=4, centers=ce)
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    ref = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=O.num_threads())
+    assert_same(ix.searchBatch(k, Q), ref, "m=16 large batch")
