@@ -1160,28 +1160,11 @@ static int prepare_fast(mmidx_index *ix) {
     return MMIDX_OK;
 }
 
-// CTAs per query of the fused scan (each takes every nsplit-th probe): 592 CTAs are resident (148 SMs x 4), so a
-// batch that fills only a few waves is split further to even out the last wave -- 1250 queries (a 10 000-query batch
-// over 8 query groups) run as 3 x 1250 CTAs in 7 waves of a third of the work instead of 3 full waves.  Every extra
-// split costs its own prologue / final phase and the merge kernel (~4 % each, measured scale).
-// mmidx_search's pipelined chunks run on two streams: the tail of one chunk's grid is filled by the next chunk's
-// kernels, so splitting a >= 1-wave chunk only adds work there
-static thread_local bool g_overlapped_chunks = false;
-
+// CTAs per query of the fused scan (each takes every nsplit-th probe): one, unless the batch cannot fill the 592
+// resident CTA slots (148 SMs x 4).  Splitting larger batches to even out the last wave was measured and rejected: the
+// partial results need k_merge_topk (0.36 ms for 2500 queries x 2 parts), more than the tail it saves.
 static int fast_nsplit(int64_t nq, int w) {
-    const double slots = 148.0 * 4.0;
-    if ((double)nq >= 6.0 * slots || (g_overlapped_chunks && (double)nq >= slots)) return 1;
-    int best = 1;
-    double best_cost = 1e300;
-    for (int ns = 1; ns <= std::min(w, 16); ++ns) {
-        const double waves = std::ceil((double)nq * ns / slots);
-        const double cost = waves / ns * (1.0 + 0.04 * (ns - 1));
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best = ns;
-        }
-    }
-    return best;
+    return (int)std::min<int64_t>(w, std::max<int64_t>(1, (148 * 4 + nq - 1) / nq));
 }
 
 template <int CAP32, int M>
@@ -1656,9 +1639,7 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
         if (rc != MMIDX_OK) break;
         cudaStream_t cs = (c & 1) ? sc2 : st;
         cudaStreamWaitEvent(cs, ev[2 * c], 0);
-        g_overlapped_chunks = true;
         rc = search_dev_impl(ix, nb, dQ + q0 * ix->p.d, k, diids + q0 * k, ddist + q0 * k, nullptr, nullptr, dcnt + q0, cs, false);
-        g_overlapped_chunks = false;
         if (rc != MMIDX_OK) break;
         mk(ev[2 * c + 1], cs);
         if (rc != MMIDX_OK) break;

@@ -377,7 +377,7 @@ def test_barrier_free_sweep_overflow_is_rolled_back(monkeypatch):
     Cq = np.zeros((nlist, d))
     Cq[:, 0] = [0.0, 6.0, 12.0, 18.0]  # a query near the origin ranks the lists 0, 1, 2, 3
     Q = rng.normal(0, 0.3, size=(6, d))
-    Q = np.vstack([Q] * 600)            # 3600 queries: one CTA per query (no probe splitting)
+    Q = np.vstack([Q] * 120)            # > 592 queries: one CTA per query (no probe splitting)
     q0 = Q[0]
 
     def pick(l, nearest, count, width):
