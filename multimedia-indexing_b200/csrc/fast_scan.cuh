@@ -207,6 +207,18 @@ struct __align__(16) ProbeHdr {
 static_assert(sizeof(ProbeHdr) == 32, "ProbeHdr layout");
 __host__ __device__ constexpr int fast_desc_stride(int m) { return (int)sizeof(ProbeHdr) + 4 * m; }
 
+// flat PQ index as pseudo lists: probes[q][p] = p for every query; iids[i] = i
+__global__ void k_fill_flat_probes(int64_t nq, int w, int32_t *__restrict__ probes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * w) probes[i] = (int32_t)(i % w);
+}
+__global__ void k_iota_negate(int64_t n_iota, int32_t *__restrict__ iota, int64_t n_neg, const double *__restrict__ src,
+                              double *__restrict__ neg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_iota) iota[i] = (int32_t)i;
+    if (i < n_neg) neg[i] = -src[i];
+}
+
 struct FastArgs {
     const double *Q;          // [nq][d]
     const double *C;          // [nlist][d]
@@ -230,6 +242,7 @@ struct FastArgs {
     const int32_t *ocnt;      // [nq]
     const unsigned char *desc;  // [nq][w] probe descriptors in oprobes order (ProbeHdr + s[m]), k_fast_prep
     int d, m, ks, S, w, k, nsplit;
+    int flat;                   // flat PQ index: every (pseudo) list shares coarse row 0 (a zero centroid)
     int resolve_ties;           // 1: replay the queue's tie rule inside the kernel (unsharded, nsplit == 1)
     int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
     int32_t *fb_count;
@@ -547,7 +560,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
                                                         const float *__restrict__ t1max, const float *__restrict__ pmax,
                                                         const int64_t *__restrict__ list_off,
                                                         const int32_t *__restrict__ list_len, int d, int m_rt, int S_rt,
-                                                        int w, unsigned char *__restrict__ desc, double *__restrict__ bq,
+                                                        int w, int flat, unsigned char *__restrict__ desc, double *__restrict__ bq,
                                                         int32_t *__restrict__ oprobes, int32_t *__restrict__ ocnt) {
     const int m = MT > 0 ? MT : m_rt;
     const int S = ST > 0 ? ST : S_rt;
@@ -595,7 +608,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
                 h.start = list_off[l];
                 h.len = len;
                 h.p = p;
-                h.l = l;
+                h.l = flat ? 0 : l;  // row of C / T1 / t1max
                 h.pad[0] = h.pad[1] = h.pad[2] = 0;
                 *reinterpret_cast<ProbeHdr *>(dq + (int64_t)slot * dstride) = h;
             }
@@ -613,7 +626,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
             const int e = e0 + sub;
             const bool valid = e < w * m;
             const int p = valid ? e / m : 0, j = valid ? e - p * m : 0;
-            const int l = pr[p];
+            const int l = flat ? 0 : pr[p];
             const int slot = slot_of[p];
             const bool use = valid && slot >= 0;
             int src = j * S + t;
@@ -631,7 +644,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
     } else {
         for (int e = tid; e < w * m; e += MMIDX_NT) {
             const int p = e / m, j = e - p * m;
-            const int l = pr[p];
+            const int l = flat ? 0 : pr[p];
             const int slot = slot_of[p];
             if (slot < 0) continue;
             const double *Cl = C + (int64_t)l * d;
@@ -1038,7 +1051,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_ivfpq_scan_direct(FastArgs a, Topk
             const int l = pr[p];
             const int64_t start = a.list_off[l];
             const int len = a.list_len[l];
-            const double *Cl = a.C + (int64_t)l * a.d;
+            const double *Cl = a.C + (int64_t)(a.flat ? 0 : l) * a.d;
             for (int base = 0; base < len; base += ROUND) {
                 tk.maybe_compact(a.k);
                 const double thr = tk.thr;
@@ -1067,6 +1080,7 @@ struct TieDirectArgs {
     const int64_t *list_off;
     const int32_t *list_len;
     int d, m, ks, S, w, k, code_bytes;
+    int flat;
 };
 
 __global__ void __launch_bounds__(MMIDX_NT) k_tie_collect_ivfpq_direct(TieDirectArgs a, const double *__restrict__ res_dist,
@@ -1082,7 +1096,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_tie_collect_ivfpq_direct(TieDirect
         for (int p = 0; p < a.w && found < a.k; ++p) {
             const int l = a.probes[q * a.w + p];
             const int64_t start = a.list_off[l];
-            const double *Cl = a.C + (int64_t)l * a.d;
+            const double *Cl = a.C + (int64_t)(a.flat ? 0 : l) * a.d;
             const uint8_t *cp = a.codes + start * a.code_bytes;
             const int32_t *li = a.iids + start;
             const TieDirectArgs &r = a;

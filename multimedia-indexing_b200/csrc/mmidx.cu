@@ -160,6 +160,8 @@ struct mmidx_index {
     int last_launches = 0;
     // fast path tables (fast_scan.cuh), rebuilt when a quantizer or the permutation changes
     DevBuf dT1, dP32t, dt1max, dpmax, dstats;
+    DevBuf dPneg;             // flat PQ on the fused path: -P (the index is an IVFPQ with one zero centroid, fast_scan.cuh)
+    int flat_nlist = 0;       // ... and its pseudo lists of equal length
     DevBuf dC32, dc2, dcmax;  // coarse_fast.cuh: fp32 copy of the coarse quantizer, ||C||^2, max ||C||
     std::vector<int32_t> shard_map;  // optional list -> owning shard (default l % shard_count)
     bool fast_ready = false;
@@ -591,6 +593,7 @@ extern "C" int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, 
         CK(cudaStreamSynchronize(st));
         ix->n_local += n;
         ix->n += n;
+        ix->sealed = false;
         return MMIDX_OK;
     }
     for (int64_t i = 0; i < n; ++i)
@@ -1130,7 +1133,11 @@ static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, co
 // fast path (fast_scan.cuh): fp32 filter + exact verification, no ADC tables in HBM
 // ---------------------------------------------------------------------------------------------------------
 static bool fast_eligible(const mmidx_index *ix) {
-    if (ix->p.type != MMIDX_IVFPQ || ix->force_exact) return false;
+    if (ix->force_exact) return false;
+    // a flat PQ index runs the same kernels as an IVFPQ with ONE zero centroid and the negated codebook:
+    // (0 - q) - (-P) = -(q - P) exactly, so every squared term has the bits of PQ.computeLookupADC (PQ.java:387-399)
+    if (ix->p.type == MMIDX_PQ && ix->shard_count > 1) return false;
+    if (ix->p.type != MMIDX_IVFPQ && ix->p.type != MMIDX_PQ) return false;
     // the fused kernel is specialised for byte codes with full 256-entry sub-tables and 8 or 16 sub-quantizers
     if (ix->p.ks != 256 || (ix->p.m != 8 && ix->p.m != 16)) return false;
     if (ix->p.d > 2048) return false;  // query + one survivor's squared terms must fit next to the collectors
@@ -1140,7 +1147,18 @@ static bool fast_eligible(const mmidx_index *ix) {
 static int prepare_fast(mmidx_index *ix) {
     if (ix->fast_ready) return MMIDX_OK;
     cudaStream_t st = ix->stream;
-    const int m = ix->p.m, ks = ix->p.ks, S = ix->S, nlist = ix->p.nlist, d = ix->p.d;
+    const bool flat = ix->p.type == MMIDX_PQ;
+    const int m = ix->p.m, ks = ix->p.ks, S = ix->S, nlist = flat ? 1 : ix->p.nlist, d = ix->p.d;
+    const double *P = ix->dP.as<double>();
+    if (flat) {
+        const int64_t np = (int64_t)m * ks * S;
+        RET(ix->dPneg.reserve(sizeof(double) * (size_t)np, 0, st));
+        RET(ix->dC.reserve(sizeof(double) * (size_t)d, 0, st));
+        CK(cudaMemsetAsync(ix->dC.p, 0, sizeof(double) * (size_t)d, st));
+        k_iota_negate<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(0, nullptr, np, P, ix->dPneg.as<double>());
+        RET(post_launch("k_iota_negate", nullptr));
+        P = ix->dPneg.as<double>();
+    }
     RET(ix->dT1.reserve(sizeof(float) * (size_t)nlist * m * ks, 0, st));
     RET(ix->dP32t.reserve(sizeof(float) * (size_t)m * ks * S, 0, st));
     RET(ix->dt1max.reserve(sizeof(float) * (size_t)nlist * m, 0, st));
@@ -1150,13 +1168,71 @@ static int prepare_fast(mmidx_index *ix) {
     CK(cudaMemsetAsync(ix->dpmax.p, 0, sizeof(float) * (size_t)m, st));
     CK(cudaMemsetAsync(ix->dstats.p, 0, sizeof(unsigned long long) * 4, st));
     const int32_t *perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
-    k_build_t1<<<dim3(nlist, m), MMIDX_NT, sizeof(double) * (size_t)S, st>>>(ix->dC.as<double>(), ix->dP.as<double>(), perm, d, m,
-                                                                          ks, S, ix->dT1.as<float>(), ix->dt1max.as<float>());
+    k_build_t1<<<dim3(nlist, m), MMIDX_NT, sizeof(double) * (size_t)S, st>>>(ix->dC.as<double>(), P, perm, d, m, ks, S,
+                                                                          ix->dT1.as<float>(), ix->dt1max.as<float>());
     RET(post_launch("k_build_t1", nullptr));
-    k_build_p32t<<<m, MMIDX_NT, 0, st>>>(ix->dP.as<double>(), m, ks, S, ix->dP32t.as<float>(), ix->dpmax.as<float>());
+    k_build_p32t<<<m, MMIDX_NT, 0, st>>>(P, m, ks, S, ix->dP32t.as<float>(), ix->dpmax.as<float>());
     RET(post_launch("k_build_p32t", nullptr));
     CK(cudaStreamSynchronize(st));
     ix->fast_ready = true;
+    return MMIDX_OK;
+}
+
+// Flat PQ index -> pseudo inverted lists of equal length L (iid order, so probe rank then list position is the
+// reference's offer order, PQ.java:303-319) plus the bank-conflict-aware copy the fused kernel scans.
+static int seal_pq_fast(mmidx_index *ix) {
+    if (ix->sealed) return MMIDX_OK;
+    cudaStream_t st = ix->stream;
+    const int64_t n = ix->n_local;
+    const int m = ix->p.m, cb = ix->code_bytes;
+    const int64_t L = std::max<int64_t>(16384, (((n + MMIDX_MAX_K - 1) / MMIDX_MAX_K) + 15) & ~(int64_t)15);
+    const int nl = (int)((n + L - 1) / L);
+    ix->h_list_off.assign((size_t)nl + 1, 0);
+    ix->h_list_len.assign((size_t)std::max(nl, 1), 0);
+    for (int l = 0; l < nl; ++l) {
+        ix->h_list_off[l] = (int64_t)l * L;
+        ix->h_list_len[l] = (int32_t)std::min<int64_t>(L, n - (int64_t)l * L);
+    }
+    ix->h_list_off[nl] = n;
+    ix->fast_len_ok = L < ((int64_t)1 << FAST_POS_BITS);
+    ix->flat_nlist = nl;
+    if (nl > 0 && ix->fast_len_ok) {
+        RET(ix->dlist_off.reserve(sizeof(int64_t) * (size_t)(nl + 1), 0, st));
+        RET(ix->dlist_len.reserve(sizeof(int32_t) * (size_t)nl, 0, st));
+        CK(cudaMemcpyAsync(ix->dlist_off.p, ix->h_list_off.data(), sizeof(int64_t) * (size_t)(nl + 1), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->dlist_len.p, ix->h_list_len.data(), sizeof(int32_t) * (size_t)nl, cudaMemcpyHostToDevice, st));
+        RET(ix->csr_iids.reserve(sizeof(int32_t) * (size_t)n, 0, st));
+        k_iota_negate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ix->csr_iids.as<int32_t>(), 0, nullptr, nullptr);
+        RET(post_launch("k_iota_negate", nullptr));
+        RET(ix->csr_ocodes.reserve((size_t)n * cb, 0, st));
+        RET(ix->csr_oiids.reserve((size_t)n * sizeof(int32_t), 0, st));
+        RET(ix->csr_orank.reserve((size_t)n * sizeof(int32_t), 0, st));
+        Scratch sc(st);
+        int32_t *src;
+        RET(sc.get(&src, (size_t)n));
+        if (ix->reorder) {
+            const size_t rsm = (size_t)RCH * m;
+            if (m == 8) {
+                RET(set_smem(k_reorder_lists<8>, rsm));
+                k_reorder_lists<8><<<nl, MMIDX_NT, rsm, st>>>(ix->dcodes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
+                                                             ix->dlist_len.as<int32_t>(), src);
+            } else {
+                RET(set_smem(k_reorder_lists<16>, rsm));
+                k_reorder_lists<16><<<nl, MMIDX_NT, rsm, st>>>(ix->dcodes.as<uint8_t>(), ix->dlist_off.as<int64_t>(),
+                                                              ix->dlist_len.as<int32_t>(), src);
+            }
+            RET(post_launch("k_reorder_lists", nullptr));
+        } else {
+            k_identity_order<<<nl, MMIDX_NT, 0, st>>>(ix->dlist_off.as<int64_t>(), ix->dlist_len.as<int32_t>(), src);
+            RET(post_launch("k_identity_order", nullptr));
+        }
+        k_apply_order<<<nl, MMIDX_NT, 0, st>>>(ix->dcodes.as<uint8_t>(), ix->csr_iids.as<int32_t>(), ix->dlist_off.as<int64_t>(),
+                                              ix->dlist_len.as<int32_t>(), src, m, ix->csr_ocodes.as<uint8_t>(),
+                                              ix->csr_oiids.as<int32_t>(), ix->csr_orank.as<int32_t>());
+        RET(post_launch("k_apply_order", nullptr));
+        CK(cudaStreamSynchronize(st));
+    }
+    ix->sealed = true;
     return MMIDX_OK;
 }
 
@@ -1193,14 +1269,16 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     FastArgs a{};
     a.Q = dQ;
     a.C = ix->dC.as<double>();
-    a.P = ix->dP.as<double>();
+    const bool flat = ix->p.type == MMIDX_PQ;
+    a.flat = flat ? 1 : 0;
+    a.P = flat ? ix->dPneg.as<double>() : ix->dP.as<double>();
     a.T1 = ix->dT1.as<float>();
     a.P32t = ix->dP32t.as<float>();
     a.t1max = ix->dt1max.as<float>();
     a.pmax = ix->dpmax.as<float>();
     a.perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
     a.probes = dprobes;
-    a.codes = ix->csr_codes.as<uint8_t>();
+    a.codes = flat ? ix->dcodes.as<uint8_t>() : ix->csr_codes.as<uint8_t>();  // flat: the append log is the one list order
     a.iids = ix->csr_iids.as<int32_t>();
     a.ocodes = ix->csr_ocodes.as<uint8_t>();
     a.oiids = ix->csr_oiids.as<int32_t>();
@@ -1230,11 +1308,11 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         StageMark sm(ix, st, 1);
         const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)w * 4 + 16;
         if (M == 8 && a.S == 16)
-            k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, desc, bq, oprobes, ocnt);
+            k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt);
         else if (M == 16 && a.S == 8)
-            k_fast_prep<16, 8><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, desc, bq, oprobes, ocnt);
+            k_fast_prep<16, 8><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt);
         else
-            k_fast_prep<0, 0><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, desc, bq, oprobes, ocnt);
+            k_fast_prep<0, 0><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt);
         RET(post_launch("k_fast_prep", launches));
         {
             dim3 g2((unsigned)((nq + T2_QB - 1) / T2_QB), M);
@@ -1321,6 +1399,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         t.w = w;
         t.k = k;
         t.code_bytes = ix->code_bytes;
+        t.flat = a.flat;
         const int tg = (int)std::min<int64_t>(nq, 296);
         k_tie_collect_ivfpq_direct<<<tg, MMIDX_NT, 0, st>>>(t, res.dist, amb_list, amb_count, tl);
         RET(post_launch("k_tie_collect_ivfpq_direct", launches));
@@ -1369,7 +1448,13 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(seal(ix));
     }
-    const bool fast = fast_eligible(ix) && ix->fast_len_ok && k <= 256;  // otherwise: exact ADC-table kernels
+    if (ix->p.type == MMIDX_PQ && fast_eligible(ix) && k <= 256 && !ix->sealed) {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        RET(seal_pq_fast(ix));
+    }
+    // otherwise: exact ADC-table kernels
+    const bool fast = fast_eligible(ix) && ix->fast_len_ok && k <= 256 && (ix->p.type != MMIDX_PQ || ix->flat_nlist > 0);
+    if (ix->p.type == MMIDX_PQ && fast) w = ix->flat_nlist;  // every pseudo list is probed, in iid order
     if (fast && !ix->fast_ready) {
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(prepare_fast(ix));
@@ -1384,6 +1469,8 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
     if (ix->p.type == MMIDX_IVFPQ && fast) {
         // scratch is the coarse distance matrix only: [nq][nlist] binary64, bounded to 1 GiB
         qchunk = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / ((size_t)ix->p.nlist * sizeof(double))));
+    } else if (ix->p.type == MMIDX_PQ && fast) {
+        qchunk = 32768;  // T2 (m KB) + w probe descriptors per query
     } else if (ix->p.type == MMIDX_IVFPQ) {
         size_t per_q = (size_t)w * ix->p.m * ix->p.ks * sizeof(double);
         qchunk = std::max<int64_t>(1, (int64_t)(ix->lut_chunk_bytes / per_q));
@@ -1418,6 +1505,16 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
             }
                 break;
             case MMIDX_PQ:
+                if (fast) {
+                    int32_t *fp;  // probes[q][p] = p
+                    r = sc.get(&fp, (size_t)nb * w);
+                    if (r != MMIDX_OK) break;
+                    k_fill_flat_probes<<<(unsigned)((nb * w + 255) / 256), 256, 0, st>>>(nb, w, fp);
+                    r = post_launch("k_fill_flat_probes", &launches);
+                    if (r != MMIDX_OK) break;
+                    r = ivfpq_chunk_fast_dispatch(ix, dq, nb, k, w, res, nullptr, amb_list, amb_count, true, st, &launches, fp);
+                    break;
+                }
                 r = big ? pq_chunk<2048>(ix, dq, nb, k, res, amb_list, amb_count, st, &launches)
                         : pq_chunk<1024>(ix, dq, nb, k, res, amb_list, amb_count, st, &launches);
                 break;

@@ -124,17 +124,34 @@ def test_ivfpq_vs_oracle(case, mode, monkeypatch):
     assert (l2 == ol[:100]).all() and (c2 == oc[:100]).all() and ix.getLoadCounter() == n
 
 
-@pytest.mark.parametrize("d,m,ks,n,nq,k", [(32, 4, 64, 7000, 20, 10), (128, 8, 256, 30000, 16, 100), (16, 2, 1000, 2000, 8, 5)])
-def test_pq_vs_oracle(d, m, ks, n, nq, k):
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+@pytest.mark.parametrize("d,m,ks,n,nq,k,use_perm", [
+    (32, 4, 64, 7000, 20, 10, False),
+    (128, 8, 256, 30000, 16, 100, False),    # configs[1] geometry: the fused fp32-filter kernel over pseudo lists
+    (128, 8, 256, 40000, 700, 100, True),    # ... one CTA per query, three pseudo lists, RandomPermutation
+    (64, 16, 256, 20000, 40, 256, False),    # m = 16, k at the fast path's limit
+    (16, 2, 1000, 2000, 8, 5, False)])
+def test_pq_vs_oracle(d, m, ks, n, nq, k, use_perm, mode, monkeypatch):
+    # "fast": a flat index with ks = 256, m in {8, 16} is searched as an IVFPQ with one zero centroid and the negated
+    # codebook (same bits); "exact": the binary64 table kernel for every geometry
+    monkeypatch.setenv("MMIDX_MODE", mode)
     ce = synth.mixture_centers(d, 64)
     X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
     P = synth.train_pq(d, m, ks, ntrain=min(n, 5000), iters=4, centers=ce)
+    perm = M.random_permutation(3, d) if use_perm else None
     pq = M.PQ(d, n, m, ks)
     pq.loadProductQuantizer(P)
-    _, codes = pq.indexVectors(None, X, return_codes=True)
-    oc = O.pq_encode(P, X, threads=8)
-    assert (codes == oc).all()
-    assert_same(pq.searchBatch(k, Q), O.pq_search(P, oc, Q, k, threads=8), "pq")
+    if perm is not None:
+        pq.setPermutation(perm)
+    _, codes = pq.indexVectors(None, X[:n // 2], return_codes=True)
+    oc = O.pq_encode(P, X, perm, threads=8)
+    assert (codes == oc[:n // 2]).all()
+    ref_half = O.pq_search(P, oc[:n // 2], Q, k, perm, threads=8)
+    assert_same(pq.searchBatch(k, Q), ref_half, "pq, first half")
+    pq.indexVectors(None, X[n // 2:])  # an add after a search re-seals the pseudo lists
+    assert_same(pq.searchBatch(k, Q), O.pq_search(P, oc, Q, k, perm, threads=8), "pq")
+    if perm is not None:
+        return
     luts = pq.computeLookupADC(Q[:3])
     for i in range(3):
         assert (luts[i] == O.pq_lut(P, Q[i])).all()
