@@ -71,6 +71,7 @@ def main():
     # ---- a9 PQ encode + a6 PQ flat ADC scan: configs[1] ----
     pq = M.PQ(d, 1_000_000, m, ks)
     pq.loadProductQuantizer(Pf)
+    pq.encode(X[:100_000])  # warm-up (context, scratch pool)
     t0 = time.perf_counter()
     _, codes = pq.indexVectors(None, X, return_codes=True)
     gs = time.perf_counter() - t0
@@ -92,6 +93,7 @@ def main():
     ix.loadCoarseQuantizer(Cq)
     ix.loadProductQuantizer(Pr)
     ix.setW(32)
+    ix.encode(X[:100_000])  # warm-up
     t0 = time.perf_counter()
     lists, codes = ix.indexVectors(None, X, return_codes=True)
     gs = time.perf_counter() - t0
