@@ -1,5 +1,5 @@
 // offline study of orderings inside an inverted list (M = 8): wavefronts per warp-wide lookup.
-// Inputs: codes.bin / off.bin / freq.bin dumped from the bench index by scratch/make_cache.py + the snippet in profiles/README.md
+// Inputs: codes.bin / off.bin / freq.bin written to /tmp/sim by scratch/make_cache.py (the bench index); build: gcc -O2 -o sim sim_reorder.c
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
