@@ -219,6 +219,33 @@ __global__ void k_iota_negate(int64_t n_iota, int32_t *__restrict__ iota, int64_
     if (i < n_neg) neg[i] = -src[i];
 }
 
+// Launch order of a batch that fills only a few waves of CTAs: heaviest queries first (longest-processing-time rule),
+// so the last wave is made of short CTAs.  One CTA, nq <= ORDER_MAX; bitonic sort of (work desc, query asc).
+constexpr int ORDER_MAX = 4096;
+constexpr int ORDER_NT = 1024;
+__global__ void __launch_bounds__(ORDER_NT) k_order_queries(int nq, const int32_t *__restrict__ work, int32_t *__restrict__ qorder) {
+    __shared__ unsigned long long key[ORDER_MAX];
+    int n2 = 1;
+    while (n2 < nq) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += ORDER_NT)
+        key[i] = i < nq ? ((unsigned long long)(0x7fffffffu - (unsigned)work[i]) << 32) | (unsigned)i : ~0ull;
+    for (int size = 2; size <= n2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n2 >> 1); t += ORDER_NT) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a > b) == up) {
+                    key[lo] = b;
+                    key[hi] = a;
+                }
+            }
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq; i += ORDER_NT) qorder[i] = (int32_t)(key[i] & 0xffffffffu);
+}
+
 struct FastArgs {
     const double *Q;          // [nq][d]
     const double *C;          // [nlist][d]
@@ -240,6 +267,7 @@ struct FastArgs {
     const float *T2;          // [nq][m*256] per-query term of the table decomposition (k_fast_t2)
     const int32_t *oprobes;   // [nq][w]     ranks of the probes with a non-empty list on this shard, ascending
     const int32_t *ocnt;      // [nq]
+    const int32_t *qorder;    // [nq] query handled by CTA row y (k_order_queries), or NULL: y itself
     const unsigned char *desc;  // [nq][w] probe descriptors in oprobes order (ProbeHdr + s[m]), k_fast_prep
     int d, m, ks, S, w, k, nsplit;
     int flat;                   // flat PQ index: every (pseudo) list shares coarse row 0 (a zero centroid)
@@ -561,7 +589,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
                                                         const int64_t *__restrict__ list_off,
                                                         const int32_t *__restrict__ list_len, int d, int m_rt, int S_rt,
                                                         int w, int flat, unsigned char *__restrict__ desc, double *__restrict__ bq,
-                                                        int32_t *__restrict__ oprobes, int32_t *__restrict__ ocnt) {
+                                                        int32_t *__restrict__ oprobes, int32_t *__restrict__ ocnt,
+                                                        int32_t *__restrict__ work) {
     const int m = MT > 0 ? MT : m_rt;
     const int S = ST > 0 ? ST : S_rt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -590,6 +619,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
     // probe ranks with a non-empty list on this shard, in rank order (lists other shards own have length 0 here)
     if (tid < 32) {
         int base = 0;
+        long long cand = 0;  // candidates this query will scan on this shard
         for (int p0 = 0; p0 < w; p0 += 32) {
             const int p = p0 + tid;
             int l = 0, len = 0;
@@ -597,6 +627,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
                 l = pr[p];
                 len = list_len[l];
             }
+            cand += len;
             const bool own = len > 0;
             const unsigned mk = __ballot_sync(0xffffffffu, own);
             if (p < w) slot_of[p] = -1;
@@ -614,7 +645,12 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
             }
             base += __popc(mk);
         }
-        if (tid == 0) ocnt[q] = base;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
+        if (tid == 0) {
+            ocnt[q] = base;
+            if (work) work[q] = (int32_t)min(cand, (long long)0x7fffffff);
+        }
     }
     __syncthreads();
     if (ST > 0) {
@@ -780,7 +816,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
 
     const int tid = threadIdx.x;
     const int s = blockIdx.x;
-    const int64_t q = blockIdx.y;
+    const int64_t q = a.qorder ? (int64_t)a.qorder[blockIdx.y] : (int64_t)blockIdx.y;
     const unsigned char *dq = a.desc + q * (int64_t)a.w * DSTRIDE;
     const uint32_t t1_bytes = (uint32_t)(nent * sizeof(float));
     const int S = a.S;

@@ -1239,6 +1239,10 @@ static int seal_pq_fast(mmidx_index *ix) {
 // CTAs per query of the fused scan (each takes every nsplit-th probe): one, unless the batch cannot fill the 592
 // resident CTA slots (148 SMs x 4).  Splitting larger batches to even out the last wave was measured and rejected: the
 // partial results need k_merge_topk (0.36 ms for 2500 queries x 2 parts), more than the tail it saves.
+// set while mmidx_search's pipelined chunks are being enqueued: they alternate between two streams, so the tail of one
+// chunk's grid is filled by the next chunk's kernels and re-ordering the queries of a chunk only costs a kernel
+static thread_local bool g_overlapped_chunks = false;
+
 static int fast_nsplit(int64_t nq, int w) {
     return (int)std::min<int64_t>(w, std::max<int64_t>(1, (148 * 4 + nq - 1) / nq));
 }
@@ -1298,22 +1302,33 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         // per-(query, probe) terms of the table decomposition and the per-query error radius
         unsigned char *desc;
         double *bq;
-        int32_t *oprobes, *ocnt;
+        int32_t *oprobes, *ocnt, *work = nullptr, *qorder = nullptr;
         float *T2;
         RET(sc.get(&T2, (size_t)nq * M * 256));
         RET(sc.get(&desc, (size_t)nq * w * fast_desc_stride(M)));
         RET(sc.get(&bq, (size_t)nq));
         RET(sc.get(&oprobes, (size_t)nq * w));
         RET(sc.get(&ocnt, (size_t)nq));
+        // a batch of 1 .. 7 waves of CTAs is launched heaviest query first (the tail of the last wave gets short)
+        const bool lpt = nsplit == 1 && nq > 148 * 4 && nq <= ORDER_MAX && !g_overlapped_chunks;
+        if (lpt) {
+            RET(sc.get(&work, (size_t)nq));
+            RET(sc.get(&qorder, (size_t)nq));
+        }
         StageMark sm(ix, st, 1);
         const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)w * 4 + 16;
         if (M == 8 && a.S == 16)
-            k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt);
+            k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt, work);
         else if (M == 16 && a.S == 8)
-            k_fast_prep<16, 8><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt);
+            k_fast_prep<16, 8><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt, work);
         else
-            k_fast_prep<0, 0><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt);
+            k_fast_prep<0, 0><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt, work);
         RET(post_launch("k_fast_prep", launches));
+        if (lpt) {
+            k_order_queries<<<1, ORDER_NT, 0, st>>>((int)nq, work, qorder);
+            RET(post_launch("k_order_queries", launches));
+        }
+        a.qorder = qorder;
         {
             dim3 g2((unsigned)((nq + T2_QB - 1) / T2_QB), M);
             const size_t sm2 = (size_t)T2_QB * a.S * sizeof(float);
@@ -1736,7 +1751,9 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
         if (rc != MMIDX_OK) break;
         cudaStream_t cs = (c & 1) ? sc2 : st;
         cudaStreamWaitEvent(cs, ev[2 * c], 0);
+        g_overlapped_chunks = true;
         rc = search_dev_impl(ix, nb, dQ + q0 * ix->p.d, k, diids + q0 * k, ddist + q0 * k, nullptr, nullptr, dcnt + q0, cs, false);
+        g_overlapped_chunks = false;
         if (rc != MMIDX_OK) break;
         mk(ev[2 * c + 1], cs);
         if (rc != MMIDX_OK) break;

@@ -319,6 +319,13 @@ class HybridIVFPQ:
                 check(lib.mmidx_search_dev(self.index._h, n_loc, _p(dq), k, _p(b["s_iids"]), _p(b["s_dist"]), _p(b["s_cnt"]), st))
         if self.R == 1:
             return b["s_iids"][:nq], b["s_dist"][:nq], b["s_cnt"][:nq]
+        if self.S == 1:
+            # every rank is a whole query group: its slice is one contiguous block of each output array, so the three
+            # results are all-gathered in place (no pack / unpack kernels around the collective)
+            dist.all_gather_into_tensor(b["iids"].view(-1), b["s_iids"].view(-1))
+            dist.all_gather_into_tensor(b["dist"].view(-1), b["s_dist"].view(-1))
+            dist.all_gather_into_tensor(b["cnt"], b["s_cnt"])
+            return b["iids"][:nq], b["dist"][:nq], b["cnt"][:nq]
         fo, fs, loc = b["fo"], b["fs"], b["loc"]
         loc[fo[0]:fo[0] + fs[0]].copy_(b["s_iids"].view(torch.uint8).view(-1))
         loc[fo[1]:fo[1] + fs[1]].copy_(b["s_dist"].view(torch.uint8).view(-1))

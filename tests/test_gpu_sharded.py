@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
         import mmidx_b200 as M
         import pyoracle as O
         from multimedia_indexing_b200 import synth
-        from multimedia_indexing_b200.sharded import ShardedIVFPQ
+        from multimedia_indexing_b200.sharded import HybridIVFPQ, ShardedIVFPQ
 
         ok = True
         msgs = []
@@ -61,6 +61,25 @@ def _worker(rank, world, port, q):
             msgs.append(f"{case}: equal={bool(same)} local_vectors={int(sh.listSizes().sum())}")
             ok &= int(sh.listSizes().sum()) < n  # really sharded
             sh.close()
+        # HybridIVFPQ: S list shards x R query groups; S = 1 all-gathers every group's slice in place (the layout
+        # bench.py picks for an index that fits one GPU's L2), S = world is the pure list sharding above
+        d, m, ks, nlist, w, k, n, nq = 64, 8, 256, 64, 16, 100, 30000, 1501  # odd nq: ragged last slice
+        ce = synth.mixture_centers(d, 128)
+        X, Q = synth.mixture(n, d, 1, ce), synth.mixture(nq, d, 2, ce)
+        Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=5000, iters=3, centers=ce)
+        for S in (1, world):
+            hy = HybridIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist, S)
+            hy.loadCoarseQuantizer(Cq)
+            hy.loadProductQuantizer(P)
+            hy.setW(w)
+            lists, codes = hy.indexAll(X)
+            iids, dd, cnt = hy.search(k, torch.from_numpy(Q).cuda())
+            off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+            oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=8)
+            same = (iids.cpu().numpy() == oi).all() and (dd.cpu().numpy() == od).all() and (cnt.cpu().numpy() == oc).all()
+            ok &= bool(same)
+            msgs.append(f"hybrid S={S}: equal={bool(same)}")
+            hy.index.close()
         q.put((rank, ok, msgs))
         dist.destroy_process_group()
     except Exception as e:  # pragma: no cover
