@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -200,10 +201,25 @@ struct DeviceGuard {
     }
 };
 
+// opt-in dynamic shared memory of a kernel; the attribute call takes a driver lock (~10 us), so the largest size set
+// per (device, kernel) is remembered and the call is skipped on the hot path
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
     if (bytes > 227 * 1024) return fail(MMIDX_ERR_UNSUPPORTED, "kernel needs %zu bytes of shared memory", bytes);
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> done;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    const auto key = std::make_pair(dev, reinterpret_cast<const void *>(kernel));
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = done.find(key);
+        if (it != done.end() && it->second >= bytes) return MMIDX_OK;
+    }
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &v = done[key];
+    v = std::max(v, bytes);
     return MMIDX_OK;
 }
 
