@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -86,17 +87,71 @@ struct DevBuf {
 };
 
 // stream-ordered scratch, released (stream-ordered) when the call returns
+// Per-(index, stream) scratch arena of the search hot path: one grow-only device block with stack (bump / rollback)
+// allocation, so a search call issues no cudaMallocAsync / cudaFreeAsync once the arena has seen its batch size (a
+// search call makes ~25 scratch allocations; at small per-GPU batches the call is host-bound, profiles/README.md).
+// Re-use across calls is safe because consecutive calls on one stream are stream-ordered; a second host thread that
+// finds the arena busy falls back to stream-ordered allocations.
+struct Arena {
+    void *base = nullptr;
+    size_t cap = 0, off = 0, peak = 0;
+    int depth = 0;
+    std::thread::id owner;
+};
+
 struct Scratch {
     cudaStream_t st;
-    std::vector<void *> ptrs;
+    std::vector<void *> ptrs;  // stream-ordered allocations that did not come from an arena
+    Arena *ar = nullptr;
+    std::mutex *amu = nullptr;
+    size_t mark = 0;
     explicit Scratch(cudaStream_t s) : st(s) {}
+    Scratch(cudaStream_t s, std::map<cudaStream_t, Arena> &arenas, std::mutex &mu) : st(s) {
+        std::lock_guard<std::mutex> lk(mu);
+        Arena &a = arenas[s];
+        if (a.depth == 0 || a.owner == std::this_thread::get_id()) {
+            a.owner = std::this_thread::get_id();
+            a.depth++;
+            ar = &a;  // std::map nodes are stable
+            amu = &mu;
+            mark = a.off;
+        }
+    }
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
     ~Scratch() {
         for (void *p : ptrs) cudaFreeAsync(p, st);
+        if (!ar) return;
+        std::lock_guard<std::mutex> lk(*amu);
+        ar->off = mark;
+        if (--ar->depth == 0 && ar->peak > ar->cap) {  // outermost scope: grow for the next call
+            if (ar->base) cudaFreeAsync(ar->base, st);
+            ar->base = nullptr;
+            ar->cap = 0;
+            const size_t want = ar->peak + ar->peak / 4;
+            void *p = nullptr;
+            if (cudaMallocAsync(&p, want, st) == cudaSuccess) {
+                ar->base = p;
+                ar->cap = want;
+            } else {
+                cudaGetLastError();
+            }
+            ar->peak = 0;
+        }
     }
     template <typename T>
     int get(T **out, size_t count) {
+        size_t bytes = (std::max<size_t>(count * sizeof(T), 16) + 255) & ~(size_t)255;
+        if (ar) {
+            const size_t o = ar->off;
+            ar->off += bytes;
+            ar->peak = std::max(ar->peak, ar->off);
+            if (ar->off <= ar->cap) {
+                *out = reinterpret_cast<T *>(static_cast<unsigned char *>(ar->base) + o);
+                return MMIDX_OK;
+            }
+        }
         void *p = nullptr;
-        size_t bytes = std::max<size_t>(count * sizeof(T), 16);
         CK(cudaMallocAsync(&p, bytes, st));
         ptrs.push_back(p);
         *out = reinterpret_cast<T *>(p);
@@ -153,6 +208,8 @@ struct mmidx_index {
     std::vector<int32_t> h_list_len;
     std::vector<int64_t> h_list_off;
     cudaStream_t stream = nullptr;
+    std::map<cudaStream_t, Arena> arenas;  // search scratch per launching stream (Scratch)
+    std::mutex arena_mu;
     // mmidx_search: copies overlap the kernels of other chunks; chunks alternate between `stream` and `comp2_stream`
     // so that the tail of one chunk's scan overlaps the next chunk's kernels
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr, comp2_stream = nullptr;
@@ -301,6 +358,9 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
             cudaMemcpy(h, ix->dstats.p, sizeof(h), cudaMemcpyDeviceToHost);
             fprintf(stderr, "[mmidx stats] candidates=%llu rescanned_lists=%llu survivors=%llu direct_fallbacks=%llu\n", h[0], h[1], h[2], h[3]);
         }
+        cudaDeviceSynchronize();
+        for (auto &kv : ix->arenas)
+            if (kv.second.base) cudaFree(kv.second.base);
         if (ix->stream) {
             cudaStreamSynchronize(ix->stream);
             cudaStreamDestroy(ix->stream);
@@ -1278,7 +1338,7 @@ template <int CAP32, int M>
 static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k, int w, const ResultBufs &res,
                             double *res_tie, int32_t *amb_list, int32_t *amb_count, bool resolve_ties, cudaStream_t st,
                             int *launches, const int32_t *given_probes) {
-    Scratch sc(st);
+    Scratch sc(st, ix->arenas, ix->arena_mu);
     int32_t *dprobes = const_cast<int32_t *>(given_probes);
     if (!dprobes) {
         RET(sc.get(&dprobes, (size_t)nq * w));
@@ -1493,7 +1553,7 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
     int launches = 0;
     ix->timer.reset();
     StageMark whole(ix, st, 4);
-    Scratch sc(st);
+    Scratch sc(st, ix->arenas, ix->arena_mu);
     int32_t *amb_list, *amb_count;
     const int d = ix->p.d;
     int64_t qchunk = nq;
@@ -1718,7 +1778,7 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
     if (nq == 0) return MMIDX_OK;
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
-    Scratch sc(st);
+    Scratch sc(st, ix->arenas, ix->arena_mu);
     double *dQ, *ddist;
     int32_t *diids, *dcnt;
     RET(sc.get(&dQ, (size_t)nq * ix->p.d));
