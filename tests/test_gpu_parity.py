@@ -237,6 +237,12 @@ def test_bulk_reload_matches_incremental_index():
     b.indexPQCodes(None, lists[1010:], codes[1010:])
     ra, rb = a.searchBatch(k, Q), b.searchBatch(k, Q)
     assert (ra[0] == rb[0]).all() and (ra[1] == rb[1]).all()
+    # through the reference's "ivfadc" tuple format (persistence.py: what a Java host would write to / scan from BDB)
+    from multimedia_indexing_b200 import persistence
+    c = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    assert persistence.load_ivfpq(c, persistence.ivfpq_records(lists, codes, ks), batch=700) == len(X)
+    rc = c.searchBatch(k, Q)
+    assert (ra[0] == rc[0]).all() and (ra[1] == rc[1]).all() and (c.listSizes() == a.listSizes()).all()
     # search, add more, search again: re-seal keeps insertion order
     a.indexVectors(None, X[:500] + 1.0)
     X2 = np.vstack([X, X[:500] + 1.0])
