@@ -3,9 +3,10 @@ Importing the package loads libmmidx.so and fails loudly if it is not built (no 
 from . import _capi
 from ._capi import MmidxError, LIB_PATH
 from .datastructures import Answer, IVFPQ, PQ, Linear, TransformationType, random_permutation
-from .aggregation import VladAggregator
+from .aggregation import VladAggregator, VladAggregatorMultipleVocabularies, normalizeL2, normalizePower, normalizeSSR
 
-__all__ = ["Answer", "IVFPQ", "PQ", "Linear", "TransformationType", "VladAggregator", "MmidxError", "random_permutation",
+__all__ = ["Answer", "IVFPQ", "PQ", "Linear", "TransformationType", "VladAggregator", "VladAggregatorMultipleVocabularies", "normalizeL2", "normalizePower", "normalizeSSR",
+           "MmidxError", "random_permutation",
            "LIB_PATH"]
 
 
