@@ -391,6 +391,17 @@ def run_gpu(args, rank, world, local_rank):
         parity["ids_equal_to_oracle"] = bool((oi == r_iids[:sample]).all())
         parity["dist_bit_equal_to_oracle"] = bool((od == r_dist[:sample]).all())
         parity["max_rel_dist_err"] = float(np.max(np.abs(od - r_dist[:sample]) / np.maximum(od, 1e-300)))
+    elif world > 1 and not args.no_cpu_baseline:
+        # multi-GPU lines: the merged result of a bounded query sample against the oracle (rank 0, untimed)
+        try:
+            O, off, cc, ii = cpu_oracle_setup(X, Cq, P, prefix, lists, codes)
+            ns = 256
+            oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q[:ns], TOPK, W_PROBE, threads=O.num_threads())
+            parity["sample_queries"] = ns
+            parity["ids_equal_to_oracle"] = bool((oi == r_iids[:ns]).all())
+            parity["dist_bit_equal_to_oracle"] = bool((od == r_dist[:ns]).all())
+        except Exception as e:  # never let the checker break a scaling line
+            parity["oracle_sample_error"] = repr(e)[:200]
 
     out = {
         "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
