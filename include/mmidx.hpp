@@ -7,8 +7,8 @@
 // (J/ = src/main/java/gr/iti/mklab/visual/).  Checked exceptions become mmidx::Exception(message); the id <-> internal
 // id maps the reference keeps in BDB JE stay on the host side as in-memory maps.  Header-only; link with -lmmidx.
 //
-// Status of this file: compiled and linked in the CPU test suite (tests/test_cpp_mirror.py builds
-// tests/cpp/mirror_check.cpp and checks the no-device error path); it has not been run on a GPU in round 1.
+// Checked by tests/test_cpp_mirror.py, which builds tests/cpp/mirror_check.cpp: error paths and the no-device failure on
+// CPU, a Linear / VladAggregator round trip on a B200.
 #pragma once
 #include <chrono>
 #include <cstdint>
