@@ -9,9 +9,11 @@ vectors, m=8, ks=256, nlist=1024, nprobe (w)=32, top-100.
 
 A step = one pass of the search path over one batch of NQ queries.  `value` = device-resident queries/s
 (CUDA events on the launching stream), `e2e` = the same through the host C-ABI call mmidx_search with pinned
-HOST buffers (H2D of the queries and D2H of ids+distances inside the timed region).  N > 1: the IVF lists are
-sharded over the ranks (l % N == rank), per-shard top-k all-gathered over NCCL and merged on the device;
-total work is fixed, so scaling is "strong"."""
+HOST buffers (H2D of the queries and D2H of ids+distances inside the timed region).  N > 1: S list shards x R query
+groups (multimedia-indexing_b200/sharded.py): the lists are sharded only until one shard's codes fit half of the L2
+(S = 1 for this 12 MB index: every rank searches nq/N queries over the whole index and the results are all-gathered
+over NCCL; MMIDX_LIST_SHARDS forces list sharding with the per-shard top-k exchange and device merge).  Total work is
+fixed, so scaling is "strong"."""
 import argparse
 import ctypes as C
 import json
