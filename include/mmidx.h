@@ -88,6 +88,9 @@ int mmidx_add(mmidx_t *ix, int64_t n, const double *X, int32_t *out_list, void *
 int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, const void *codes);
 /* encode only, nothing stored (the arithmetic of indexVectorInternal without the append) */
 int mmidx_encode(mmidx_t *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes);
+/* mmidx_add with the vectors already in HBM: dX[n][d], d_out_list / d_out_codes are DEVICE pointers (may be NULL).
+ * Lets a caller index a database that is produced on the device (bench.py configs[3]: 10M vectors per shard). */
+int mmidx_add_dev(mmidx_t *ix, int64_t n, const double *dX, int32_t *d_out_list, void *d_out_codes);
 
 /* ---- search: computeNearestNeighborsInternal(k, double[]) (IVFPQ.java:408-450 computeKnnIVFADC,
  * PQ.java:290-322 computeKnnADC, Linear.java:138-163) for nq queries Q[nq][d].
@@ -127,6 +130,37 @@ int mmidx_tie_collect_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32
 int mmidx_tie_finish_dev(int64_t nq, int32_t k, int32_t nparts, const int64_t *d_l_seq, const int32_t *d_l_iid,
                          const int32_t *d_l_eq, const int32_t *d_l_cnt, const int32_t *d_amb_list,
                          const int32_t *d_amb_count, int32_t *d_res_iids, double *d_res_dist, void *stream);
+
+/* ---- multi-GPU, whole step inside the library (one process per GPU of ONE NVSwitch node, world <= 8) ----
+ * The job is G = S x R ranks, rank = group * S + shard: S list shards hold one copy of the index (this index must have
+ * been created with shard_count = S, shard_rank = rank % S), R groups each serve their own query batch.  The
+ * exchange does not go through a collective library: every rank owns an exchange window in HBM which its peers map
+ * over CUDA IPC, and the kernels that produce a row (coarse verification, fused ADC scan, merge, tie pass) store it
+ * straight into the window of the rank that consumes it over NVLink; the exchange points are epoch flags in the same
+ * windows (csrc/comm.cuh).  The reference's single queue for all probed lists (IVFPQ.java:409,445) is rebuilt by the
+ * owner of a query slice from the S per-shard queues, including the ordered tie rule.
+ *   1. every rank: mmidx_comm_create -> 128-byte handle;  2. all-gather the handles with any host-side transport;
+ *   3. every rank: mmidx_comm_attach(handles[world]);     4. mmidx_search_multi_dev / mmidx_search_multi per step. */
+#define MMIDX_COMM_HANDLE_BYTES 128
+/* max_gq / k_max size the window: the largest group batch and k that will be searched */
+int mmidx_comm_create(mmidx_t *ix, int32_t rank, int32_t world, int32_t list_shards, int64_t max_gq, int32_t k_max,
+                      void *handle_out /* MMIDX_COMM_HANDLE_BYTES */);
+int mmidx_comm_attach(mmidx_t *ix, const void *handles /* [world][MMIDX_COMM_HANDLE_BYTES], by rank */);
+int mmidx_comm_destroy(mmidx_t *ix);
+/* One step: the gq queries dQ[gq][d] of this rank's GROUP (every shard of a group passes the same queries; every rank of
+ * the job must call with the same gq, k, gather_all, the same number of times).  Asynchronous on `stream`.
+ * Results live in this rank's window (valid until the second next step on this stream): job-wide arrays
+ * iids[R * gqp][k], dist[R * gqp][k], count[R * gqp] with gqp = S * ceil(gq / S); group g's query q is row g * gqp + q.
+ * This rank produced rows [*row0, *row0 + *nrows) (its slice of its group's batch; the whole batch when S == 1);
+ * gather_all != 0 additionally delivers every rank's rows to every rank (stores into all windows + one more
+ * exchange point), so the arrays are complete everywhere. */
+int mmidx_search_multi_dev(mmidx_t *ix, int64_t gq, const double *dQ, int32_t k, int32_t gather_all,
+                           const int32_t **d_iids, const double **d_dist, const int32_t **d_count, int64_t *row0,
+                           int64_t *nrows, void *stream);
+/* same with HOST buffers: copies the group's queries in, runs the step, copies THIS rank's rows out
+ * (queries [*first_query, *first_query + *nrows) of the group batch) and synchronises */
+int mmidx_search_multi(mmidx_t *ix, int64_t gq, const double *Q, int32_t k, int32_t *out_iids, double *out_dist,
+                       int32_t *out_count, int64_t *first_query, int64_t *nrows);
 
 /* IVFPQ.computeNearestCoarseIndices IVFPQ.java:575-601: out[nq][w], ascending coarse distance */
 int mmidx_coarse_probe(mmidx_t *ix, int64_t nq, const double *Q, int32_t w, int32_t *out);

@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("MMIDX_LIB_PATH") or os.path.join(_HERE, "libmmidx.so"
 MMIDX_LINEAR, MMIDX_PQ, MMIDX_IVFPQ = 0, 1, 2
 OK, ERR_INVALID, ERR_DIM, ERR_FULL, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED, ERR_W = range(8)
 MAX_K = 1024
+COMM_HANDLE_BYTES = 128
 
 
 class Params(C.Structure):
@@ -55,6 +56,13 @@ _SIGS = {
     "mmidx_add": [_vp, _i64, _vp, _vp, _vp],
     "mmidx_add_codes": [_vp, _i64, _vp, _vp],
     "mmidx_encode": [_vp, _i64, _vp, _vp, _vp],
+    "mmidx_add_dev": [_vp, _i64, _vp, _vp, _vp],
+    "mmidx_comm_create": [_vp, _i32, _i32, _i32, _i64, _i32, _vp],
+    "mmidx_comm_attach": [_vp, _vp],
+    "mmidx_comm_destroy": [_vp],
+    "mmidx_search_multi_dev": [_vp, _i64, _vp, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                               C.POINTER(_i64), C.POINTER(_i64), _vp],
+    "mmidx_search_multi": [_vp, _i64, _vp, _i32, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i64)],
     "mmidx_search": [_vp, _i64, _vp, _i32, _vp, _vp, _vp],
     "mmidx_search_dev": [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
     "mmidx_search_shard_dev": [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

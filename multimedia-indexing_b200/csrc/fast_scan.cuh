@@ -512,7 +512,8 @@ __device__ __forceinline__ double exact_adc(const double *__restrict__ Cl, const
                                             const uint8_t *__restrict__ code, int m, int ks, int S) {
     double dist = 0.0;
     for (int j = 0; j < m; ++j) {
-        const double *pc = P + ((int64_t)j * ks + code[j]) * S;
+        const int c = (ks <= 256) ? (int)code[j] : (int)reinterpret_cast<const uint16_t *>(code)[j];
+        const double *pc = P + ((int64_t)j * ks + c) * S;
         double acc = 0.0;
         for (int t = 0; t < S; ++t) {
             int src = j * S + t;

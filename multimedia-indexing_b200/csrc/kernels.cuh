@@ -150,7 +150,27 @@ __global__ void __launch_bounds__(MMIDX_NT) k_assign_nearest(const double *__res
 
 // ------------------------------------------------------------------------------------------------------
 // Result sink shared by every top-k kernel: part-major arrays [nq][nparts][k].
+//
+// Multi-GPU (comm.cuh): a sink can also deliver the row straight into the HBM of peer GPUs (NVLink P2P stores into
+// the peers' exchange windows), so the per-shard top-k / the final rows travel from the kernel that produces them --
+// there is no pack kernel, no staging buffer and no collective launch on the data path.
+//   mode 1 (ROUTE): the row of group query gq goes ONLY to the window of its slice owner, peer gq / sl
+//   mode 2 (BCAST): the row is written locally (iids/dist/... below) AND copied to every peer in base[]
 // ------------------------------------------------------------------------------------------------------
+constexpr int MMIDX_MAX_PEERS = 8;
+enum { SINK_IIDS = 1, SINK_DIST = 2, SINK_SEQ = 4, SINK_CNT = 8, SINK_TIE = 16 };
+
+struct PeerSink {
+    int mode;       // 0: local only
+    int npeer;      // ROUTE: number of slice owners (list shards); BCAST: number of remote peers
+    int sl;         // ROUTE: queries per owner slice
+    int fields;     // SINK_* mask of the arrays the peers receive
+    long long q0;   // index of this launch's query 0 inside the group batch
+    long long row0; // ROUTE: first row of this shard's block in an owner's arrays; BCAST: row of group query 0
+    unsigned char *base[MMIDX_MAX_PEERS];  // peer windows (parity offset applied by the host)
+    long long off_iids, off_dist, off_seq, off_cnt, off_tie;  // byte offsets of the destination arrays in a window
+};
+
 struct TopkOut {
     int32_t *iids;            // [nq][nparts][k]
     double *dist;             // [nq][nparts][k]
@@ -160,25 +180,73 @@ struct TopkOut {
     int32_t *amb_list;        // final stage only: queries whose k-th boundary tie was cut (or NULL)
     int32_t *amb_count;
     int nparts;
+    PeerSink sink;            // nparts == 1 whenever sink.mode != 0
 };
+
+// copies row `row` (k entries taken from the getters) into the windows of peers [p0, p1)
+template <typename GI, typename GD, typename GS>
+__device__ __forceinline__ void sink_row(const PeerSink &ps, int p0, int p1, long long row, int k, int n, double tiev,
+                                         GI gi, GD gd, GS gs) {
+    for (int i = threadIdx.x; i < k; i += MMIDX_NT) {
+        const bool v = i < n;
+        const int32_t iv = v ? gi(i) : -1;
+        const double dv = v ? gd(i) : __longlong_as_double(0x7ff0000000000000LL);
+        const unsigned long long sv = v ? gs(i) : 0ull;
+        for (int p = p0; p < p1; ++p) {
+            unsigned char *b = ps.base[p];
+            if (ps.fields & SINK_IIDS) reinterpret_cast<int32_t *>(b + ps.off_iids)[row * k + i] = iv;
+            if (ps.fields & SINK_DIST) reinterpret_cast<double *>(b + ps.off_dist)[row * k + i] = dv;
+            if (ps.fields & SINK_SEQ) reinterpret_cast<unsigned long long *>(b + ps.off_seq)[row * k + i] = sv;
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int p = p0; p < p1; ++p) {
+            unsigned char *b = ps.base[p];
+            if (ps.fields & SINK_CNT) reinterpret_cast<int32_t *>(b + ps.off_cnt)[row] = n;
+            if (ps.fields & SINK_TIE) reinterpret_cast<double *>(b + ps.off_tie)[row] = tiev;
+        }
+    }
+}
+
+// destination of group query q of this launch: peers [p0, p1) and the row inside their arrays
+__device__ __forceinline__ long long sink_dest(const PeerSink &ps, int64_t q, int &p0, int &p1) {
+    const long long gq = q + ps.q0;
+    if (ps.mode == 1) {
+        p0 = (int)(gq / ps.sl);
+        p1 = p0 + 1;
+        return ps.row0 + (gq - (long long)p0 * ps.sl);
+    }
+    p0 = 0;
+    p1 = ps.npeer;
+    return ps.row0 + gq;
+}
 
 // writes the first n (<= k) entries of a collector that is already in output order (finalize() / sort_first())
 template <int CAP>
 __device__ void write_sorted(TopK<CAP> &tk, const TopkOut &o, int64_t q, int part, int k, int n, bool amb) {
-    const int64_t base = (q * o.nparts + part) * (int64_t)k;
-    for (int i = threadIdx.x; i < k; i += MMIDX_NT) {
-        bool v = i < n;
-        o.iids[base + i] = v ? tk.pay[i] : -1;
-        o.dist[base + i] = v ? tk.dist[i] : __longlong_as_double(0x7ff0000000000000LL);
-        if (o.seq) o.seq[base + i] = v ? tk.seq[i] : 0ull;
-    }
-    if (threadIdx.x == 0) {
-        o.cnt[q * o.nparts + part] = n;
-        if (o.tie) o.tie[q * o.nparts + part] = (n == k && amb) ? tk.dist[n - 1] : -1.0;
-        if (o.amb_list && amb) {
-            int slot = atomicAdd(o.amb_count, 1);
-            o.amb_list[slot] = (int32_t)q;
+    const double tiev = (n == k && amb) ? tk.dist[n - 1] : -1.0;
+    if (o.sink.mode != 1) {
+        const int64_t base = (q * o.nparts + part) * (int64_t)k;
+        for (int i = threadIdx.x; i < k; i += MMIDX_NT) {
+            bool v = i < n;
+            o.iids[base + i] = v ? tk.pay[i] : -1;
+            o.dist[base + i] = v ? tk.dist[i] : __longlong_as_double(0x7ff0000000000000LL);
+            if (o.seq) o.seq[base + i] = v ? tk.seq[i] : 0ull;
         }
+        if (threadIdx.x == 0) {
+            o.cnt[q * o.nparts + part] = n;
+            if (o.tie) o.tie[q * o.nparts + part] = tiev;
+        }
+    }
+    if (threadIdx.x == 0 && o.amb_list && amb) {
+        int slot = atomicAdd(o.amb_count, 1);
+        o.amb_list[slot] = (int32_t)q;
+    }
+    if (o.sink.mode != 0) {
+        int p0, p1;
+        const long long row = sink_dest(o.sink, q, p0, p1);
+        sink_row(o.sink, p0, p1, row, k, n, tiev, [&](int i) { return tk.pay[i]; }, [&](int i) { return tk.dist[i]; },
+                 [&](int i) { return tk.seq[i]; });
     }
 }
 
@@ -510,27 +578,18 @@ __global__ void __launch_bounds__(MMIDX_NT) k_merge_topk(MergeArgs a, TopkOut o)
     }
     bool amb;
     const int n = tk.finalize(a.k, &amb);
-    const int64_t base = q * (int64_t)a.k;
-    for (int i = threadIdx.x; i < a.k; i += MMIDX_NT) {
-        bool v = i < n;
-        o.iids[base + i] = v ? tk.pay[i] : -1;
-        o.dist[base + i] = v ? tk.dist[i] : __longlong_as_double(0x7ff0000000000000LL);
-        if (o.seq) o.seq[base + i] = v ? tk.seq[i] : 0ull;
-    }
+    // a part that discarded candidates tied at distance t makes the answer ambiguous iff t == final T
+    // (T <= every part's own k-th distance, so comparing each part's value with T is exact)
+    __shared__ int s_amb;
     if (threadIdx.x == 0) {
-        o.cnt[q] = n;
-        // a part that discarded candidates tied at distance t makes the answer ambiguous iff t == final T
-        // (T <= every part's own k-th distance, so comparing each part's value with T is exact)
         if (a.tie && n == a.k) {
             for (int part = 0; part < a.nparts; ++part)
                 if (a.tie[(int64_t)part * a.part_stride + q * a.q_stride] == tk.dist[n - 1]) amb = true;
         }
-        if (o.tie) o.tie[q] = (n == a.k && amb) ? tk.dist[n - 1] : -1.0;
-        if (o.amb_list && amb) {
-            int slot = atomicAdd(o.amb_count, 1);
-            o.amb_list[slot] = (int32_t)q;
-        }
+        s_amb = amb ? 1 : 0;
     }
+    __syncthreads();
+    write_sorted(tk, o, q, 0, a.k, n, s_amb != 0);  // o.nparts == 1
 }
 
 // ------------------------------------------------------------------------------------------------------

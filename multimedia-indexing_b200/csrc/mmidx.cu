@@ -19,12 +19,15 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
+#include <unistd.h>
 #include <vector>
 
 #include "kernels.cuh"
 #include "tie_resolve.cuh"
 #include "coarse_fast.cuh"
 #include "fast_scan.cuh"
+#include "comm.cuh"
 
 using namespace mmidx;
 
@@ -97,6 +100,8 @@ struct Arena {
     size_t cap = 0, off = 0, peak = 0;
     int depth = 0;
     std::thread::id owner;
+    uint64_t gen = 0;       // bumped whenever the block is re-allocated (captured CUDA graphs hold its addresses)
+    uint64_t spills = 0;    // allocations that did not fit and went to cudaMallocAsync
 };
 
 struct Scratch {
@@ -128,6 +133,7 @@ struct Scratch {
             if (ar->base) cudaFreeAsync(ar->base, st);
             ar->base = nullptr;
             ar->cap = 0;
+            ar->gen++;
             const size_t want = ar->peak + ar->peak / 4;
             void *p = nullptr;
             if (cudaMallocAsync(&p, want, st) == cudaSuccess) {
@@ -150,6 +156,7 @@ struct Scratch {
                 *out = reinterpret_cast<T *>(static_cast<unsigned char *>(ar->base) + o);
                 return MMIDX_OK;
             }
+            ar->spills++;
         }
         void *p = nullptr;
         CK(cudaMallocAsync(&p, bytes, st));
@@ -169,6 +176,13 @@ struct StageTimer {
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
     bool enabled = false;
+    bool capturing = false;  // the stream is being captured into a CUDA graph: events become external record nodes
+    void record(cudaEvent_t e, cudaStream_t st) const {
+        if (capturing)
+            cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+        else
+            cudaEventRecord(e, st);
+    }
     cudaEvent_t get() {
         if (used == pool.size()) {
             cudaEvent_t e;
@@ -227,9 +241,22 @@ struct mmidx_index {
     bool force_exact = false;  // MMIDX_MODE=exact
     bool want_stats = false;   // MMIDX_STATS=1
     size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
+    int sm_count = 148;        // SMs of this device: grids are sized in CTA slots = sm_count x resident CTAs per SM
+    uint64_t gen = 0;          // bumped by everything that invalidates captured search graphs
+    bool use_graph = true;     // MMIDX_GRAPH=0: always enqueue kernel by kernel
+    std::map<struct GraphKey, struct GraphEntry> *graphs = nullptr;
+    std::mutex graph_mu;
+    std::vector<cudaEvent_t> ev_pool;  // mmidx_search's pipeline events, re-used across calls
+    std::mutex ev_mu;
+    struct Comm *comm = nullptr;       // multi-GPU exchange (mmidx_comm_*)
 };
 
+// CTA slots of the device for kernels that keep 4 CTAs per SM resident (the fused scan's launch bound)
+static inline int cta_slots(const mmidx_index *ix) { return ix->sm_count * 4; }
+
 static bool fast_eligible(const mmidx_index *ix);
+static void drop_graphs(mmidx_index *ix);
+static void comm_release(mmidx_index *ix);
 
 static int check_device(int device) {
     int cnt = 0;
@@ -280,6 +307,14 @@ static int set_smem(K kernel, size_t bytes) {
     return MMIDX_OK;
 }
 
+// SM count of the current device (for entry points that take no index)
+static int current_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        return 148;
+    return n;
+}
+
 static int post_launch(const char *name, int *launches) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MMIDX_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
@@ -322,6 +357,11 @@ extern "C" int mmidx_create(const mmidx_params *pp, mmidx_t **out) {
         delete ix;
         return fail(MMIDX_ERR_INVALID, "shard_rank out of range");
     }
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) ix->sm_count = prop.multiProcessorCount;
+    }
+    if (const char *e = getenv("MMIDX_GRAPH")) ix->use_graph = atoi(e) != 0;
     if (const char *e = getenv("MMIDX_MODE")) ix->force_exact = strcmp(e, "exact") == 0;
     if (const char *e = getenv("MMIDX_STATS")) ix->want_stats = atoi(e) != 0;
     if (const char *e = getenv("MMIDX_REORDER")) ix->reorder = atoi(e) != 0;
@@ -359,6 +399,9 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
             fprintf(stderr, "[mmidx stats] candidates=%llu rescanned_lists=%llu survivors=%llu direct_fallbacks=%llu\n", h[0], h[1], h[2], h[3]);
         }
         cudaDeviceSynchronize();
+        drop_graphs(ix);
+        for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
+        comm_release(ix);
         for (auto &kv : ix->arenas)
             if (kv.second.base) cudaFree(kv.second.base);
         if (ix->stream) {
@@ -398,6 +441,7 @@ extern "C" int mmidx_set_product_quantizer(mmidx_t *ix, const double *P) {
     CK(cudaStreamSynchronize(ix->stream));
     ix->has_P = true;
     ix->fast_ready = false;
+    ix->gen++;
     return MMIDX_OK;
 }
 
@@ -424,6 +468,7 @@ extern "C" int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C) {
     CK(cudaStreamSynchronize(ix->stream));
     ix->has_C = true;
     ix->fast_ready = false;
+    ix->gen++;
     return MMIDX_OK;
 }
 
@@ -433,6 +478,7 @@ extern "C" int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm) {
     DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->fast_ready = false;
+    ix->gen++;
     if (!perm) {
         ix->has_perm = false;
         return MMIDX_OK;
@@ -452,6 +498,7 @@ extern "C" int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm) {
 extern "C" int mmidx_set_w(mmidx_t *ix, int32_t w) {
     if (!ix) return fail(MMIDX_ERR_INVALID, "null argument");
     if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "setW applies to IVFPQ only");
+    ix->gen++;
     ix->p.w = w;  // validated at search time, like the reference (IVFPQ.java:95-97 stores it blindly)
     return MMIDX_OK;
 }
@@ -535,12 +582,32 @@ static int require_quantizers(mmidx_index *ix) {
 
 static const int64_t ADD_BATCH = 1 << 16;
 
-static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes, bool store) {
+// a failed add leaves the index as it was: the host log is truncated back to what the device log holds
+struct AddRollback {
+    mmidx_index *ix;
+    size_t hl;
+    int64_t nl;
+    bool ok = false;
+    explicit AddRollback(mmidx_index *i) : ix(i), hl(i->h_list.size()), nl(i->n_local) {}
+    ~AddRollback() {
+        if (ok) return;
+        ix->h_list.resize(hl);
+        ix->h_iid.resize(hl);
+        ix->n_local = nl;
+    }
+};
+
+// dev: X, out_list and out_codes are DEVICE pointers (mmidx_add_dev); otherwise host pointers
+static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes, bool store,
+                         bool dev = false) {
     if (!ix || (n > 0 && !X)) return fail(MMIDX_ERR_INVALID, "null argument");
     if (n < 0) return fail(MMIDX_ERR_INVALID, "n < 0");
     RET(require_quantizers(ix));
     DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lk(ix->mu);
+    AddRollback rollback(ix);
+    const cudaMemcpyKind kin = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind kout = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     // ASS.java:232-235: indexVector returns false once loadCounter >= maxNumVectors
     if (store && ix->n + n > ix->p.max_n) return fail(MMIDX_ERR_FULL, "Maximum index capacity reached");
     cudaStream_t st = ix->stream;
@@ -556,14 +623,20 @@ static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *o
         RET(sc.get(&dX, (size_t)std::min(n, ADD_BATCH) * d));
         for (int64_t b = 0; b < n; b += ADD_BATCH) {
             int64_t nb = std::min(ADD_BATCH, n - b);
-            CK(cudaMemcpyAsync(dX, X + b * d, sizeof(double) * (size_t)nb * d, cudaMemcpyHostToDevice, st));
-            k_linear_pack<<<(unsigned)((nb * d + 255) / 256), 256, 0, st>>>(dX, nb, d, ix->n + b, ix->dXb.as<double>());
+            const double *xb = X + b * d;
+            if (!dev) {
+                CK(cudaMemcpyAsync(dX, xb, sizeof(double) * (size_t)nb * d, kin, st));
+                xb = dX;
+            }
+            k_linear_pack<<<(unsigned)((nb * d + 255) / 256), 256, 0, st>>>(xb, nb, d, ix->n + b, ix->dXb.as<double>());
             RET(post_launch("k_linear_pack", &launches));
             CK(cudaStreamSynchronize(st));
         }
         ix->n += n;
         ix->n_local = ix->n;
+        ix->gen++;
         ix->last_launches = launches;
+        rollback.ok = true;
         return MMIDX_OK;
     }
     const int cb = ix->code_bytes;
@@ -581,15 +654,19 @@ static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *o
     std::vector<int64_t> hsel;
     for (int64_t b = 0; b < n; b += ADD_BATCH) {
         int64_t nb = std::min(ADD_BATCH, n - b);
-        CK(cudaMemcpyAsync(dX, X + b * d, sizeof(double) * (size_t)nb * d, cudaMemcpyHostToDevice, st));
-        RET(encode_dev(ix, dX, nb, dlist, dcodes, st, &launches));
-        if (out_codes)
-            CK(cudaMemcpyAsync((uint8_t *)out_codes + b * cb, dcodes, (size_t)nb * cb, cudaMemcpyDeviceToHost, st));
+        const double *xb = X + b * d;
+        if (!dev) {
+            CK(cudaMemcpyAsync(dX, xb, sizeof(double) * (size_t)nb * d, kin, st));
+            xb = dX;
+        }
+        RET(encode_dev(ix, xb, nb, dlist, dcodes, st, &launches));
+        if (out_codes) CK(cudaMemcpyAsync((uint8_t *)out_codes + b * cb, dcodes, (size_t)nb * cb, kout, st));
         if (ix->p.type == MMIDX_IVFPQ) {
             hl.resize(nb);
             CK(cudaMemcpyAsync(hl.data(), dlist, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+            if (out_list && dev) CK(cudaMemcpyAsync(out_list + b, dlist, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToDevice, st));
             CK(cudaStreamSynchronize(st));
-            if (out_list) memcpy(out_list + b, hl.data(), sizeof(int32_t) * (size_t)nb);
+            if (out_list && !dev) memcpy(out_list + b, hl.data(), sizeof(int32_t) * (size_t)nb);
         }
         if (store) {
             if (ix->p.type == MMIDX_PQ) {
@@ -625,13 +702,18 @@ static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *o
                     ix->n_local += ns;
                 }
             }
-            ix->sealed = false;
+            ix->sealed = false, ix->gen++;
         }
         CK(cudaStreamSynchronize(st));
     }
     if (store) ix->n += n;
     ix->last_launches = launches;
+    rollback.ok = true;
     return MMIDX_OK;
+}
+
+extern "C" int mmidx_add_dev(mmidx_t *ix, int64_t n, const double *dX, int32_t *d_out_list, void *d_out_codes) {
+    return add_or_encode(ix, n, dX, d_out_list, d_out_codes, true, true);
 }
 
 extern "C" int mmidx_add(mmidx_t *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes) {
@@ -649,6 +731,7 @@ extern "C" int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, 
     DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lk(ix->mu);
     if (ix->n + n > ix->p.max_n) return fail(MMIDX_ERR_FULL, "Maximum index capacity reached");
+    AddRollback rollback(ix);
     const int cb = ix->code_bytes;
     cudaStream_t st = ix->stream;
     // validate: code values < ks, list ids in range
@@ -669,7 +752,8 @@ extern "C" int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, 
         CK(cudaStreamSynchronize(st));
         ix->n_local += n;
         ix->n += n;
-        ix->sealed = false;
+        ix->sealed = false, ix->gen++;
+        rollback.ok = true;
         return MMIDX_OK;
     }
     for (int64_t i = 0; i < n; ++i)
@@ -701,7 +785,8 @@ extern "C" int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, 
     }
     ix->n_local += ns;
     ix->n += n;
-    ix->sealed = false;
+    ix->sealed = false, ix->gen++;
+    rollback.ok = true;
     return MMIDX_OK;
 }
 
@@ -799,15 +884,15 @@ struct StageMark {
     cudaEvent_t a = nullptr;
     int stage;
     StageMark(mmidx_index *i, cudaStream_t s, int stg) : ix(i), st(s), stage(stg) {
-        if (ix->timer.enabled) {
+        if (ix->timer.enabled && stg >= 0) {
             a = ix->timer.get();
-            cudaEventRecord(a, st);
+            ix->timer.record(a, st);
         }
     }
     void end() {
         if (a) {
             cudaEvent_t b = ix->timer.get();
-            cudaEventRecord(b, st);
+            ix->timer.record(b, st);
             ix->timer.spans.push_back({a, b, stage});
             a = nullptr;
         }
@@ -817,7 +902,7 @@ struct StageMark {
 
 // coarse stage for a chunk: D (scratch) and probes[nq][w] in queue order
 static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w, int32_t *dprobes, Scratch &sc,
-                            cudaStream_t st, int *launches) {
+                            cudaStream_t st, int *launches, const PeerSink *psink = nullptr) {
     const int nlist = ix->p.nlist, d = ix->p.d;
     double *pd;
     int32_t *pcnt, *amb_list, *amb_count;
@@ -835,6 +920,7 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     o.amb_list = amb_list;
     o.amb_count = amb_count;
     o.nparts = 1;
+    if (psink) o.sink = *psink;  // multi-GPU: the probe rows also land in the windows of the group peers
     // verification collector: the survivors are w plus the few centroids inside the error band; a small collector keeps
     // the CTA's shared memory low (8 CTAs/SM at w <= 128).  More survivors than ccap -> the kernel's exact sweep.
     const int ccap = w <= 128 ? 256 : cap_for(w);
@@ -848,7 +934,7 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     RET(sc.get(&tl.pay, (size_t)nq * w));
     RET(sc.get(&tl.eq, (size_t)nq * w));
     RET(sc.get(&tl.cnt, (size_t)nq));
-    const int tg = (int)std::min<int64_t>(nq, 296);
+    const int tg = (int)std::min<int64_t>(nq, 2 * ix->sm_count);
     if (fastc) {
         // fp32 filter (tiled FFMA GEMM) + exact binary64 verification of the few centroids inside the error band
         float *A32;
@@ -892,7 +978,8 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     }
     size_t fs = (size_t)w * 16;
     RET(set_smem(k_tie_finish, std::max<size_t>(fs, 1024 * 16)));
-    k_tie_finish<<<tg, MMIDX_NT, fs, st>>>(1, nq, w, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, dprobes, pd, nullptr);
+    k_tie_finish<<<tg, MMIDX_NT, fs, st>>>(1, nq, w, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, dprobes, pd, nullptr,
+                                           psink ? *psink : PeerSink{});
     RET(post_launch("k_tie_finish", launches));
     return MMIDX_OK;
 }
@@ -900,10 +987,10 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
 static inline int64_t lut_stride_of(const mmidx_index *ix) { return ((int64_t)ix->p.m * ix->p.ks + 1) & ~(int64_t)1; }
 
 static int launch_lut(mmidx_index *ix, const double *dQ, const int32_t *dprobes, int64_t npairs, int w, double *dlut,
-                      cudaStream_t st, int *launches) {
+                      cudaStream_t st, int *launches, bool use_perm = true) {
     if (npairs == 0) return MMIDX_OK;
     const int S = ix->S, m = ix->p.m, ks = ix->p.ks, d = ix->p.d;
-    const int32_t *perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
+    const int32_t *perm = (use_perm && ix->has_perm) ? ix->dperm.as<int32_t>() : nullptr;
     const double *C = dprobes ? ix->dC.as<double>() : nullptr;
     dim3 grid((unsigned)((npairs + LUT_PT - 1) / LUT_PT), m);
     size_t smem = (size_t)LUT_PT * S * sizeof(double);
@@ -926,6 +1013,7 @@ struct ResultBufs {
     double *dist;
     unsigned long long *seq;  // may be NULL
     int32_t *cnt;
+    PeerSink sink{};  // multi-GPU: where the final rows go besides / instead of the arrays above (kernels.cuh)
 };
 
 // merge [nq][nparts][k] partial results into res, flagging ambiguous queries
@@ -948,6 +1036,7 @@ static int launch_merge(const TopkOut &part, int nparts, int64_t nq, int k, cons
     o.dist = res.dist;
     o.seq = res.seq;
     o.cnt = res.cnt;
+        o.sink = res.sink;
     o.tie = out_tie;
     o.amb_list = amb_list;
     o.amb_count = amb_count;
@@ -994,7 +1083,7 @@ static int ivfpq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, int
     a.L.ks = ks;
     a.L.code_bytes = ix->code_bytes;
     // enough CTAs to fill the machine: split a query's probes over `nsplit` CTAs when the chunk is small
-    int nsplit = (int)std::min<int64_t>(w, std::max<int64_t>(1, (148 * 4 + nq - 1) / nq));
+    int nsplit = (int)std::min<int64_t>(w, std::max<int64_t>(1, (cta_slots(ix) + nq - 1) / nq));
     a.nsplit = nsplit;
     const size_t lut_bytes = (size_t)lut_stride_of(ix) * sizeof(double);
     const size_t smem = topk_bytes<CAP>() + 2 * lut_bytes + 64;
@@ -1009,6 +1098,7 @@ static int ivfpq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, int
         o.dist = res.dist;
         o.seq = res.seq;
         o.cnt = res.cnt;
+        o.sink = res.sink;
         o.tie = res_tie;
         o.amb_list = amb_list;
         o.amb_count = amb_count;
@@ -1049,11 +1139,11 @@ static int ivfpq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, int
         t.ks = ks;
         t.code_bytes = ix->code_bytes;
         t.k = k;
-        const int tg = (int)std::min<int64_t>(nq, 296);
+        const int tg = (int)std::min<int64_t>(nq, 2 * ix->sm_count);
         k_tie_collect_ivfpq<<<tg, MMIDX_NT, 0, st>>>(t, res.dist, amb_list, amb_count, tl);
         RET(post_launch("k_tie_collect_ivfpq", launches));
         k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count,
-                                                           res.iids, res.dist, res.seq);
+                                                           res.iids, res.dist, res.seq, res.sink);
         RET(post_launch("k_tie_finish", launches));
     }
     return MMIDX_OK;
@@ -1073,7 +1163,7 @@ static int pq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, const 
     constexpr int ROUND = TopK<CAP>::ROUND;
     const int64_t n = ix->n_local;
     int64_t rounds = std::max<int64_t>(1, (n + ROUND - 1) / ROUND);
-    int64_t want = std::max<int64_t>(1, (148 * 4 + nq - 1) / nq);
+    int64_t want = std::max<int64_t>(1, (cta_slots(ix) + nq - 1) / nq);
     int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(want, rounds));
     int64_t chunk = ((rounds + nsplit - 1) / nsplit) * ROUND;
     nsplit = (int)std::max<int64_t>(1, (n + chunk - 1) / chunk);
@@ -1099,6 +1189,7 @@ static int pq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, const 
         o.dist = res.dist;
         o.seq = res.seq;
         o.cnt = res.cnt;
+        o.sink = res.sink;
         o.tie = nullptr;
         o.amb_list = amb_list;
         o.amb_count = amb_count;
@@ -1134,11 +1225,11 @@ static int pq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, const 
     t.ks = ks;
     t.code_bytes = ix->code_bytes;
     t.k = k;
-    const int tg = (int)std::min<int64_t>(nq, 296);
+    const int tg = (int)std::min<int64_t>(nq, 2 * ix->sm_count);
     k_tie_collect_pq<<<tg, MMIDX_NT, 0, st>>>(t, res.dist, amb_list, amb_count, tl);
     RET(post_launch("k_tie_collect_pq", launches));
     k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, res.iids,
-                                                       res.dist, res.seq);
+                                                       res.dist, res.seq, res.sink);
     RET(post_launch("k_tie_finish", launches));
     return MMIDX_OK;
 }
@@ -1151,7 +1242,7 @@ static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, co
     const int64_t n = ix->n_local;
     const int d = ix->p.d;
     int64_t rounds = std::max<int64_t>(1, (n + ROUND - 1) / ROUND);
-    int64_t want = std::max<int64_t>(1, (148 * 4 + nq - 1) / nq);
+    int64_t want = std::max<int64_t>(1, (cta_slots(ix) + nq - 1) / nq);
     int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(want, rounds));
     int64_t chunk = ((rounds + nsplit - 1) / nsplit) * ROUND;
     nsplit = (int)std::max<int64_t>(1, (n + chunk - 1) / chunk);
@@ -1171,6 +1262,7 @@ static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, co
         o.dist = res.dist;
         o.seq = res.seq;
         o.cnt = res.cnt;
+        o.sink = res.sink;
         o.tie = nullptr;
         o.amb_list = amb_list;
         o.amb_count = amb_count;
@@ -1196,11 +1288,11 @@ static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, co
     RET(sc.get(&tl.pay, (size_t)nq * k));
     RET(sc.get(&tl.eq, (size_t)nq * k));
     RET(sc.get(&tl.cnt, (size_t)nq));
-    const int tg = (int)std::min<int64_t>(nq, 296);
+    const int tg = (int)std::min<int64_t>(nq, 2 * ix->sm_count);
     k_tie_collect_linear<<<tg, MMIDX_NT, 0, st>>>(dQ, a.Xb, n, d, k, res.dist, amb_list, amb_count, tl);
     RET(post_launch("k_tie_collect_linear", launches));
     k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count, res.iids,
-                                                       res.dist, res.seq);
+                                                       res.dist, res.seq, res.sink);
     RET(post_launch("k_tie_finish", launches));
     return MMIDX_OK;
 }
@@ -1319,8 +1411,8 @@ static int seal_pq_fast(mmidx_index *ix) {
 // chunk's grid is filled by the next chunk's kernels and re-ordering the queries of a chunk only costs a kernel
 static thread_local bool g_overlapped_chunks = false;
 
-static int fast_nsplit(int64_t nq, int w) {
-    return (int)std::min<int64_t>(w, std::max<int64_t>(1, (148 * 4 + nq - 1) / nq));
+static int fast_nsplit(const mmidx_index *ix, int64_t nq, int w) {
+    return (int)std::min<int64_t>(w, std::max<int64_t>(1, (cta_slots(ix) + nq - 1) / nq));
 }
 
 template <int CAP32, int M>
@@ -1345,7 +1437,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         StageMark sm(ix, st, 0);
         RET(coarse_probe_dev(ix, dQ, nq, w, dprobes, sc, st, launches));
     }
-    const int nsplit = fast_nsplit(nq, w);
+    const int nsplit = fast_nsplit(ix, nq, w);
     FastArgs a{};
     a.Q = dQ;
     a.C = ix->dC.as<double>();
@@ -1386,7 +1478,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         RET(sc.get(&oprobes, (size_t)nq * w));
         RET(sc.get(&ocnt, (size_t)nq));
         // a batch of 1 .. 7 waves of CTAs is launched heaviest query first (the tail of the last wave gets short)
-        const bool lpt = nsplit == 1 && nq > 148 * 4 && nq <= ORDER_MAX && !g_overlapped_chunks;
+        const bool lpt = nsplit == 1 && nq > cta_slots(ix) && nq <= ORDER_MAX && !g_overlapped_chunks;
         if (lpt) {
             RET(sc.get(&work, (size_t)nq));
             RET(sc.get(&qorder, (size_t)nq));
@@ -1434,6 +1526,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         o.dist = res.dist;
         o.seq = res.seq;
         o.cnt = res.cnt;
+        o.sink = res.sink;
         o.tie = res_tie;
         o.amb_list = amb_list;
         o.amb_count = amb_count;
@@ -1457,7 +1550,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         constexpr int DCAP = 1024;  // k <= 256 on this path
         const size_t dsmem = topk_bytes<DCAP>();
         RET(set_smem(k_ivfpq_scan_direct<DCAP>, dsmem));
-        const int dg = (int)std::min<int64_t>(nq * nsplit, 296);
+        const int dg = (int)std::min<int64_t>(nq * nsplit, 2 * ix->sm_count);
         k_ivfpq_scan_direct<DCAP><<<dg, MMIDX_NT, dsmem, st>>>(a, o);
         RET(post_launch("k_ivfpq_scan_direct", launches));
     }
@@ -1491,11 +1584,11 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
         t.k = k;
         t.code_bytes = ix->code_bytes;
         t.flat = a.flat;
-        const int tg = (int)std::min<int64_t>(nq, 296);
+        const int tg = (int)std::min<int64_t>(nq, 2 * ix->sm_count);
         k_tie_collect_ivfpq_direct<<<tg, MMIDX_NT, 0, st>>>(t, res.dist, amb_list, amb_count, tl);
         RET(post_launch("k_tie_collect_ivfpq_direct", launches));
         k_tie_finish<<<tg, MMIDX_NT, (size_t)k * 16, st>>>(1, nq, k, tl.seq, tl.pay, tl.eq, tl.cnt, amb_list, amb_count,
-                                                           res.iids, res.dist, res.seq);
+                                                           res.iids, res.dist, res.seq, res.sink);
         RET(post_launch("k_tie_finish", launches));
     }
     return MMIDX_OK;
@@ -1529,12 +1622,9 @@ static int validate_search(mmidx_index *ix, int64_t nq, int k, int *w_out) {
 }
 
 // device-side search over all chunks.  d_seq/d_tie non-NULL => sharded mode (no local tie resolution).
-static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k, int32_t *d_iids, double *d_dist,
-                           unsigned long long *d_seq, double *d_tie, int32_t *d_count, cudaStream_t st, bool sharded,
-                           const int32_t *d_probes = nullptr) {
-    int w = 0;
-    RET(validate_search(ix, nq, k, &w));
-    if (nq == 0) return MMIDX_OK;
+// Everything a search needs that is not per call: CSR lists sealed, fast-path tables built.  Host-synchronising, so it
+// runs before (never inside) a CUDA-graph capture.
+static int prepare_search(mmidx_index *ix, int k) {
     if (ix->p.type == MMIDX_IVFPQ && !ix->sealed) {
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(seal(ix));
@@ -1543,16 +1633,28 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(seal_pq_fast(ix));
     }
-    // otherwise: exact ADC-table kernels
     const bool fast = fast_eligible(ix) && ix->fast_len_ok && k <= 256 && (ix->p.type != MMIDX_PQ || ix->flat_nlist > 0);
-    if (ix->p.type == MMIDX_PQ && fast) w = ix->flat_nlist;  // every pseudo list is probed, in iid order
     if (fast && !ix->fast_ready) {
         std::lock_guard<std::mutex> lk(ix->mu);
         RET(prepare_fast(ix));
     }
+    return MMIDX_OK;
+}
+
+static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k, int32_t *d_iids, double *d_dist,
+                           unsigned long long *d_seq, double *d_tie, int32_t *d_count, cudaStream_t st, bool sharded,
+                           const int32_t *d_probes = nullptr, const PeerSink *sink = nullptr, bool reset_timer = true,
+                           int *launches_out = nullptr) {
+    int w = 0;
+    RET(validate_search(ix, nq, k, &w));
+    if (nq == 0) return MMIDX_OK;
+    RET(prepare_search(ix, k));
+    // otherwise: exact ADC-table kernels
+    const bool fast = fast_eligible(ix) && ix->fast_len_ok && k <= 256 && (ix->p.type != MMIDX_PQ || ix->flat_nlist > 0);
+    if (ix->p.type == MMIDX_PQ && fast) w = ix->flat_nlist;  // every pseudo list is probed, in iid order
     int launches = 0;
-    ix->timer.reset();
-    StageMark whole(ix, st, 4);
+    if (reset_timer) ix->timer.reset();
+    StageMark whole(ix, st, reset_timer ? 4 : -1);  // inside a multi-GPU step the caller brackets the whole call
     Scratch sc(st, ix->arenas, ix->arena_mu);
     int32_t *amb_list, *amb_count;
     const int d = ix->p.d;
@@ -1578,7 +1680,12 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
     for (int64_t q0 = 0; q0 < nq; q0 += qchunk) {
         int64_t nb = std::min(qchunk, nq - q0);
         CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
-        ResultBufs res{d_iids + q0 * k, d_dist + q0 * k, d_seq ? d_seq + q0 * k : nullptr, d_count + q0};
+        ResultBufs res{d_iids ? d_iids + q0 * k : nullptr, d_dist ? d_dist + q0 * k : nullptr,
+                       d_seq ? d_seq + q0 * k : nullptr, d_count ? d_count + q0 : nullptr};
+        if (sink) {
+            res.sink = *sink;
+            res.sink.q0 += q0;
+        }
         const double *dq = dQ + q0 * d;
         int r;
         const bool big = cap_for(k) == 2048;
@@ -1617,6 +1724,130 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
     }
     whole.end();
     ix->last_launches = launches;
+    if (launches_out) *launches_out += launches;
+    return MMIDX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CUDA graphs of whole search calls.  A call is ~12 kernel launches plus memsets; for small batches (one query, or
+// the 1/8 slice of a batch on 8 GPUs) the host side of those launches is longer than the kernels.  The third call with
+// the same shape and buffers is captured (the first two warm the scratch arena, whose addresses the graph holds) and
+// later calls replay it with one cudaGraphLaunch.  Anything that changes the index or re-allocates the arena
+// invalidates the captures.  parity: the multi-GPU step alternates between two window halves (comm.cuh).
+// ---------------------------------------------------------------------------------------------------------
+struct GraphKey {
+    int kind;  // 0: mmidx_search_dev, 1: multi-GPU step
+    int64_t nq;
+    int k, w, flags;
+    const void *p0, *p1, *p2, *p3;
+    cudaStream_t st;
+    bool operator<(const GraphKey &o) const {
+        return std::tie(kind, nq, k, w, flags, p0, p1, p2, p3, st) < std::tie(o.kind, o.nq, o.k, o.w, o.flags, o.p0, o.p1, o.p2, o.p3, o.st);
+    }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    int seen = 0, launches = 0;
+    bool disabled = false;
+    uint64_t gen = 0, arena_gen = 0;
+};
+
+static void drop_graphs(mmidx_index *ix) {
+    if (!ix->graphs) return;
+    for (auto &kv : *ix->graphs)
+        for (auto &e : kv.second.exec)
+            if (e) cudaGraphExecDestroy(e);
+    delete ix->graphs;
+    ix->graphs = nullptr;
+}
+
+// enqueue(int *launches) issues the call on `st`; run_graphed decides between eager issue, capture and replay
+template <typename F>
+static int run_graphed(mmidx_index *ix, GraphKey key, int parity, cudaStream_t st, F enqueue) {
+    int launches = 0;
+    if (!ix->use_graph) {
+        RET(enqueue(&launches));
+        ix->last_launches = launches;
+        return MMIDX_OK;
+    }
+    std::lock_guard<std::mutex> lk(ix->graph_mu);
+    if (!ix->graphs) ix->graphs = new std::map<GraphKey, GraphEntry>();
+    if (ix->graphs->size() > 64) {  // callers that never repeat a shape: do not accumulate
+        drop_graphs(ix);
+        ix->graphs = new std::map<GraphKey, GraphEntry>();
+    }
+    key.flags = (key.flags << 1) | (ix->timer.enabled ? 1 : 0);
+    GraphEntry &e = (*ix->graphs)[key];
+    uint64_t agen = 0, spills0 = 0;
+    {
+        std::lock_guard<std::mutex> lk2(ix->arena_mu);
+        Arena &a = ix->arenas[st];
+        agen = a.gen;
+        spills0 = a.spills;
+        if (a.depth != 0 && a.owner != std::this_thread::get_id()) e.disabled = true;  // another thread is mid-call on this stream
+    }
+    if (e.gen != ix->gen || e.arena_gen != agen) {
+        for (auto &x : e.exec)
+            if (x) cudaGraphExecDestroy(x);
+        e = GraphEntry();
+        e.gen = ix->gen;
+        e.arena_gen = agen;
+    }
+    if (e.exec[parity] && !e.disabled) {
+        CK(cudaGraphLaunch(e.exec[parity], st));
+        ix->last_launches = e.launches;
+        return MMIDX_OK;
+    }
+    if (e.disabled || e.seen < 2) {
+        e.seen++;
+        RET(enqueue(&launches));
+        ix->last_launches = launches;
+        return MMIDX_OK;
+    }
+    // capture
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        e.disabled = true;
+        RET(enqueue(&launches));
+        ix->last_launches = launches;
+        return MMIDX_OK;
+    }
+    ix->timer.capturing = true;
+    const int rc = enqueue(&launches);
+    ix->timer.capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    bool spilled;
+    {
+        std::lock_guard<std::mutex> lk2(ix->arena_mu);
+        Arena &a = ix->arenas[st];
+        spilled = a.spills != spills0 || a.gen != agen;
+    }
+    if (rc != MMIDX_OK || ce != cudaSuccess || !graph || spilled) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        e.disabled = true;  // this shape does not capture cleanly: stay eager
+        if (rc != MMIDX_OK) return rc;
+        launches = 0;
+        RET(enqueue(&launches));
+        ix->last_launches = launches;
+        return MMIDX_OK;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !exec) {
+        cudaGetLastError();
+        e.disabled = true;
+        launches = 0;
+        RET(enqueue(&launches));
+        ix->last_launches = launches;
+        return MMIDX_OK;
+    }
+    e.exec[parity] = exec;
+    e.launches = launches;
+    CK(cudaGraphLaunch(exec, st));
+    ix->last_launches = launches;
     return MMIDX_OK;
 }
 
@@ -1625,8 +1856,16 @@ extern "C" int mmidx_search_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32
     if (!ix || (nq > 0 && (!dQ || !d_iids || !d_dist || !d_count))) return fail(MMIDX_ERR_INVALID, "null argument");
     DeviceGuard g(ix->device);
     if (ix->shard_count > 1)
-        return fail(MMIDX_ERR_STATE, "sharded index: use mmidx_search_shard_dev + mmidx_merge_topk_dev");
-    return search_dev_impl(ix, nq, dQ, k, d_iids, d_dist, nullptr, nullptr, d_count, (cudaStream_t)stream, false);
+        return fail(MMIDX_ERR_STATE, "sharded index: use mmidx_search_multi_dev (or mmidx_search_shard_dev + mmidx_merge_topk_dev)");
+    int w = 0;
+    RET(validate_search(ix, nq, k, &w));
+    if (nq == 0) return MMIDX_OK;
+    RET(prepare_search(ix, k));
+    cudaStream_t st = (cudaStream_t)stream;
+    GraphKey key{0, nq, k, w, 0, dQ, d_iids, d_dist, d_count, st};
+    return run_graphed(ix, key, 0, st, [&](int *launches) {
+        return search_dev_impl(ix, nq, dQ, k, d_iids, d_dist, nullptr, nullptr, d_count, st, false, nullptr, nullptr, true, launches);
+    });
 }
 
 extern "C" int mmidx_search_shard_dev(mmidx_t *ix, int64_t nq, const double *dQ, int32_t k, const int32_t *d_probes,
@@ -1740,7 +1979,7 @@ extern "C" int mmidx_tie_collect_shard_dev(mmidx_t *ix, int64_t nq, const double
         t.ks = ks;
         t.code_bytes = ix->code_bytes;
         t.k = k;
-        k_tie_collect_ivfpq<<<(unsigned)std::min<int64_t>(nb, 296), MMIDX_NT, 0, st>>>(t, gT, gl, gcount, tl);
+        k_tie_collect_ivfpq<<<(unsigned)std::min<int64_t>(nb, 2 * ix->sm_count), MMIDX_NT, 0, st>>>(t, gT, gl, gcount, tl);
         RET(post_launch("k_tie_collect_ivfpq", &launches));
         // scatter the group's lists back to rows indexed by the original query id
         for (int64_t i = 0; i < nb; ++i) {
@@ -1763,9 +2002,9 @@ extern "C" int mmidx_tie_finish_dev(int64_t nq, int32_t k, int32_t nparts, const
     if (k < 1 || k > MMIDX_MAX_K || nparts < 1) return fail(MMIDX_ERR_INVALID, "bad geometry");
     cudaStream_t st = (cudaStream_t)stream;
     RET(set_smem(k_tie_finish, (size_t)1024 * 16));
-    k_tie_finish<<<(unsigned)std::min<int64_t>(nq, 296), MMIDX_NT, (size_t)k * 16, st>>>(
+    k_tie_finish<<<(unsigned)std::min<int64_t>(nq, 2 * current_sm_count()), MMIDX_NT, (size_t)k * 16, st>>>(
         nparts, nq, k, (const unsigned long long *)d_l_seq, d_l_iid, d_l_eq, d_l_cnt, d_amb_list, d_amb_count, d_res_iids,
-        d_res_dist, nullptr);
+        d_res_dist, nullptr, PeerSink{});
     return post_launch("k_tie_finish", nullptr);
 }
 
@@ -1790,7 +2029,12 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
     const int64_t CH = 2048;
     if (nq <= 2 * CH) {
         CK(cudaMemcpyAsync(dQ, Q, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
-        RET(search_dev_impl(ix, nq, dQ, k, diids, ddist, nullptr, nullptr, dcnt, st, false));
+        RET(prepare_search(ix, k));
+        // the device part of a small call is one graph launch (the arena hands every call the same scratch addresses)
+        GraphKey key{0, nq, k, w, 0, dQ, diids, ddist, dcnt, st};
+        RET(run_graphed(ix, key, 0, st, [&](int *launches) {
+            return search_dev_impl(ix, nq, dQ, k, diids, ddist, nullptr, nullptr, dcnt, st, false, nullptr, nullptr, true, launches);
+        }));
         CK(cudaMemcpyAsync(out_iids, diids, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out_dist, ddist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
         if (out_count) CK(cudaMemcpyAsync(out_count, dcnt, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
@@ -1807,11 +2051,28 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
     }
     cudaStream_t sh = ix->h2d_stream, sd = ix->d2h_stream, sc2 = ix->comp2_stream;
     const int nch = (int)((nq + CH - 1) / CH);
+    // events come from a per-index pool (no cudaEventCreate / Destroy on the hot path)
     std::vector<cudaEvent_t> ev((size_t)2 * nch + 1, nullptr);
     int rc = MMIDX_OK;
+    {
+        std::lock_guard<std::mutex> lk(ix->ev_mu);
+        for (auto &e : ev) {
+            if (!ix->ev_pool.empty()) {
+                e = ix->ev_pool.back();
+                ix->ev_pool.pop_back();
+            } else if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                e = nullptr;
+                rc = fail(MMIDX_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        }
+    }
     auto mk = [&](cudaEvent_t &e, cudaStream_t s_) {
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, s_) != cudaSuccess)
-            rc = fail(MMIDX_ERR_CUDA, "event: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc == MMIDX_OK && cudaEventRecord(e, s_) != cudaSuccess)
+            rc = fail(MMIDX_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(cudaGetLastError()));
+    };
+    auto ckc = [&](cudaError_t e_, const char *what) {
+        if (rc == MMIDX_OK && e_ != cudaSuccess) rc = fail(MMIDX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e_));
     };
     mk(ev[2 * nch], st);  // the scratch buffers exist (stream-ordered allocation on st)
     if (rc == MMIDX_OK && cudaStreamWaitEvent(sh, ev[2 * nch], 0) != cudaSuccess) rc = fail(MMIDX_ERR_CUDA, "cudaStreamWaitEvent");
@@ -1826,22 +2087,26 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
         mk(ev[2 * c], sh);
         if (rc != MMIDX_OK) break;
         cudaStream_t cs = (c & 1) ? sc2 : st;
-        cudaStreamWaitEvent(cs, ev[2 * c], 0);
+        ckc(cudaStreamWaitEvent(cs, ev[2 * c], 0), "cudaStreamWaitEvent");
+        if (rc != MMIDX_OK) break;
         g_overlapped_chunks = true;
         rc = search_dev_impl(ix, nb, dQ + q0 * ix->p.d, k, diids + q0 * k, ddist + q0 * k, nullptr, nullptr, dcnt + q0, cs, false);
         g_overlapped_chunks = false;
         if (rc != MMIDX_OK) break;
         mk(ev[2 * c + 1], cs);
         if (rc != MMIDX_OK) break;
-        cudaStreamWaitEvent(sd, ev[2 * c + 1], 0);
-        cudaMemcpyAsync(out_iids + q0 * k, diids + q0 * k, sizeof(int32_t) * (size_t)nb * k, cudaMemcpyDeviceToHost, sd);
-        cudaMemcpyAsync(out_dist + q0 * k, ddist + q0 * k, sizeof(double) * (size_t)nb * k, cudaMemcpyDeviceToHost, sd);
-        if (out_count) cudaMemcpyAsync(out_count + q0, dcnt + q0, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, sd);
+        ckc(cudaStreamWaitEvent(sd, ev[2 * c + 1], 0), "cudaStreamWaitEvent");
+        ckc(cudaMemcpyAsync(out_iids + q0 * k, diids + q0 * k, sizeof(int32_t) * (size_t)nb * k, cudaMemcpyDeviceToHost, sd), "cudaMemcpyAsync D2H");
+        ckc(cudaMemcpyAsync(out_dist + q0 * k, ddist + q0 * k, sizeof(double) * (size_t)nb * k, cudaMemcpyDeviceToHost, sd), "cudaMemcpyAsync D2H");
+        if (out_count) ckc(cudaMemcpyAsync(out_count + q0, dcnt + q0, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, sd), "cudaMemcpyAsync D2H");
     }
     cudaError_t e1 = cudaStreamSynchronize(sh), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(sd);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(sc2);
-    for (cudaEvent_t e : ev)
-        if (e) cudaEventDestroy(e);
+    {
+        std::lock_guard<std::mutex> lk(ix->ev_mu);
+        for (cudaEvent_t e : ev)
+            if (e) ix->ev_pool.push_back(e);
+    }
     if (rc != MMIDX_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(MMIDX_ERR_CUDA, "mmidx_search: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
@@ -1908,11 +2173,7 @@ extern "C" int mmidx_pq_lut(mmidx_t *ix, int64_t nq, const double *V, double *ou
     CK(cudaMemcpyAsync(dV, V, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
     int launches = 0;
     // computeLookupADC takes the ALREADY transformed vector (PQ.java:387): no permutation here
-    bool hp = ix->has_perm;
-    ix->has_perm = false;
-    int r = launch_lut(ix, dV, nullptr, nq, 1, dl, st, &launches);
-    ix->has_perm = hp;
-    RET(r);
+    RET(launch_lut(ix, dV, nullptr, nq, 1, dl, st, &launches, false));
     CK(cudaMemcpy2DAsync(out, row * sizeof(double), dl, stride * sizeof(double), row * sizeof(double), (size_t)nq,
                          cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -2002,6 +2263,380 @@ extern "C" int mmidx_debug_stats(mmidx_t *ix, uint64_t *out4) {
 extern "C" int mmidx_last_launches(mmidx_t *ix, int32_t *out) {
     if (!ix || !out) return fail(MMIDX_ERR_INVALID, "null argument");
     *out = ix->last_launches;
+    return MMIDX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-GPU: exchange windows over CUDA IPC + the whole sharded search step (comm.cuh)
+// ---------------------------------------------------------------------------------------------------------
+struct Comm {
+    int rank = 0, world = 1, S = 1, R = 1, shard = 0, group = 0;
+    int64_t max_gq = 0;
+    int k_max = 0, w_max = 0;
+    WinLayout L;
+    unsigned char *win = nullptr;
+    unsigned char *peer[MMIDX_MAX_PEERS] = {};
+    bool ipc_opened[MMIDX_MAX_PEERS] = {};
+    bool attached = false;
+    uint64_t calls = 0;
+    unsigned long long timeout_ns = 60ull * 1000000000ull;
+};
+
+struct CommHandle {  // what mmidx_comm_create hands out for the rendezvous (MMIDX_COMM_HANDLE_BYTES)
+    cudaIpcMemHandle_t ipc;
+    uint64_t ptr;
+    int64_t pid;
+    int32_t device, rank, world, S;
+    uint64_t bytes;
+};
+static_assert(sizeof(CommHandle) <= MMIDX_COMM_HANDLE_BYTES, "handle size");
+
+static void comm_release(mmidx_index *ix) {
+    Comm *c = ix->comm;
+    if (!c) return;
+    for (int r = 0; r < c->world && r < MMIDX_MAX_PEERS; ++r)
+        if (c->ipc_opened[r] && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->win) cudaFree(c->win);
+    delete c;
+    ix->comm = nullptr;
+}
+
+extern "C" int mmidx_comm_create(mmidx_t *ix, int32_t rank, int32_t world, int32_t list_shards, int64_t max_gq, int32_t k_max,
+                                 void *handle_out) {
+    if (!ix || !handle_out) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type != MMIDX_IVFPQ) return fail(MMIDX_ERR_INVALID, "the multi-GPU exchange is defined for IVFPQ");
+    if (world < 1 || world > MMIDX_MAX_PEERS) return fail(MMIDX_ERR_UNSUPPORTED, "world must be 1..%d (one NVSwitch node)", MMIDX_MAX_PEERS);
+    if (rank < 0 || rank >= world) return fail(MMIDX_ERR_INVALID, "rank out of range");
+    if (list_shards < 1 || world % list_shards != 0) return fail(MMIDX_ERR_INVALID, "list_shards must divide world");
+    if (ix->shard_count != list_shards || ix->shard_rank != rank % list_shards)
+        return fail(MMIDX_ERR_STATE, "index was created as shard %d of %d; rank %d of a job with %d list shards needs shard %d of %d",
+                    ix->shard_rank, ix->shard_count, rank, list_shards, rank % list_shards, list_shards);
+    if (max_gq < 1 || k_max < 1 || k_max > MMIDX_MAX_K) return fail(MMIDX_ERR_INVALID, "bad window geometry");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    comm_release(ix);
+    ix->gen++;
+    Comm *c = new Comm();
+    c->rank = rank;
+    c->world = world;
+    c->S = list_shards;
+    c->R = world / list_shards;
+    c->shard = rank % list_shards;
+    c->group = rank / list_shards;
+    c->max_gq = max_gq;
+    c->k_max = k_max;
+    c->w_max = std::min<int>(ix->p.nlist, MMIDX_MAX_K);
+    if (const char *e = getenv("MMIDX_COMM_TIMEOUT_S")) {
+        long v = atol(e);
+        if (v >= 1) c->timeout_ns = (unsigned long long)v * 1000000000ull;
+    }
+    c->L = make_layout(c->S, c->R, max_gq, k_max, c->w_max);
+    cudaError_t e = cudaMalloc((void **)&c->win, c->L.total);  // plain cudaMalloc: legacy CUDA IPC cannot export pool memory
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(MMIDX_ERR_CUDA, "cudaMalloc of the %zu-byte exchange window: %s", c->L.total, cudaGetErrorString(e));
+    }
+    ix->comm = c;
+    CK(cudaMemset(c->win, 0, c->L.data0));  // flags and epoch
+    CK(cudaDeviceSynchronize());
+    c->peer[rank] = c->win;
+    CommHandle h;
+    memset(&h, 0, sizeof(h));
+    if (world > 1) CK(cudaIpcGetMemHandle(&h.ipc, c->win));
+    h.ptr = (uint64_t)(uintptr_t)c->win;
+    h.pid = (int64_t)getpid();
+    h.device = ix->device;
+    h.rank = rank;
+    h.world = world;
+    h.S = list_shards;
+    h.bytes = c->L.total;
+    memset(handle_out, 0, MMIDX_COMM_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    if (world == 1) c->attached = true;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_comm_attach(mmidx_t *ix, const void *handles) {
+    if (!ix || !handles) return fail(MMIDX_ERR_INVALID, "null argument");
+    Comm *c = ix->comm;
+    if (!c) return fail(MMIDX_ERR_STATE, "mmidx_comm_create first");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (int r = 0; r < c->world; ++r) {
+        CommHandle h;
+        memcpy(&h, (const unsigned char *)handles + (size_t)r * MMIDX_COMM_HANDLE_BYTES, sizeof(h));
+        if (h.rank != r || h.world != c->world || h.S != c->S || h.bytes != c->L.total)
+            return fail(MMIDX_ERR_INVALID, "handle %d does not belong to this job (rank %d, world %d, shards %d, %llu bytes)", r,
+                        h.rank, h.world, h.S, (unsigned long long)h.bytes);
+        if (r == c->rank) continue;
+        if (h.pid == (int64_t)getpid()) {
+            // same process (one thread per GPU): plain peer access to the other device's allocation
+            if (h.device != ix->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(MMIDX_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", h.device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            c->peer[r] = (unsigned char *)(uintptr_t)h.ptr;
+        } else {
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return fail(MMIDX_ERR_CUDA, "cudaIpcOpenMemHandle of rank %d's window: %s", r, cudaGetErrorString(e));
+            c->peer[r] = (unsigned char *)p;
+            c->ipc_opened[r] = true;
+        }
+    }
+    c->attached = true;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_comm_destroy(mmidx_t *ix) {
+    if (!ix) return MMIDX_OK;
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(ix->mu);
+    {
+        std::lock_guard<std::mutex> lk2(ix->graph_mu);
+        drop_graphs(ix);
+    }
+    comm_release(ix);
+    ix->gen++;
+    return MMIDX_OK;
+}
+
+// one whole step of the job on this rank, enqueued on st (see comm.cuh for the stages)
+static int multi_enqueue(mmidx_index *ix, int64_t gq, const double *dQ, int k, int w, bool gather, int par, cudaStream_t st,
+                         int *launches) {
+    Comm &c = *ix->comm;
+    const WinLayout &L = c.L;
+    const int S = c.S, s = c.shard, g = c.group, d = ix->p.d;
+    const int64_t sl = (gq + S - 1) / S, gqp = sl * S;
+    auto pbase = [&](int r) { return c.peer[r] + L.data0 + (size_t)par * L.parity_stride; };
+    unsigned char *mine = pbase(c.rank);
+    unsigned *epoch = reinterpret_cast<unsigned *>(c.win + L.epoch);
+    ix->timer.reset();
+    StageMark whole(ix, st, 4);
+    k_comm_begin<<<1, 1, 0, st>>>(epoch);
+    RET(post_launch("k_comm_begin", launches));
+    auto sync = [&](int stage, bool all_ranks) -> int {
+        CommSync cs{};
+        cs.epoch = epoch;
+        cs.timeout_ns = c.timeout_ns;
+        int n = 0;
+        for (int r = 0; r < c.world; ++r) {
+            if (r == c.rank || (!all_ranks && r / S != g)) continue;
+            cs.remote[n] = reinterpret_cast<unsigned *>(c.peer[r] + L.flags) + stage * MMIDX_MAX_PEERS + c.rank;
+            cs.local[n] = reinterpret_cast<const unsigned *>(c.win + L.flags) + stage * MMIDX_MAX_PEERS + r;
+            ++n;
+        }
+        cs.n = n;
+        if (n == 0) return MMIDX_OK;
+        k_comm_sync<<<1, 32, 0, st>>>(cs);
+        return post_launch("k_comm_sync", launches);
+    };
+    // final rows of this rank: [row0, row0 + nrows) of the job-wide result arrays in (every) window
+    const int64_t row0 = (int64_t)g * gqp + (S > 1 ? (int64_t)s * sl : 0);
+    int32_t *o_iids = reinterpret_cast<int32_t *>(mine + L.o_iids) + row0 * k;
+    double *o_dist = reinterpret_cast<double *>(mine + L.o_dist) + row0 * k;
+    int32_t *o_cnt = reinterpret_cast<int32_t *>(mine + L.o_cnt) + row0;
+    PeerSink fin{};
+    if (gather && c.world > 1) {
+        fin.mode = 2;
+        fin.fields = SINK_IIDS | SINK_DIST | SINK_CNT;
+        fin.row0 = row0;
+        fin.off_iids = (long long)L.o_iids;
+        fin.off_dist = (long long)L.o_dist;
+        fin.off_cnt = (long long)L.o_cnt;
+        for (int r = 0; r < c.world; ++r)
+            if (r != c.rank) fin.base[fin.npeer++] = pbase(r);
+    }
+    if (S == 1) {
+        // replica group: the whole index is here; only the final rows travel
+        RET(search_dev_impl(ix, gq, dQ, k, o_iids, o_dist, nullptr, nullptr, o_cnt, st, false, nullptr, &fin, false, launches));
+    } else {
+        Scratch sc(st, ix->arenas, ix->arena_mu);
+        unsigned char *gb[MMIDX_MAX_PEERS];  // windows of the S members of my group, by shard
+        for (int t = 0; t < S; ++t) gb[t] = pbase(g * S + t);
+        // ---- stage 0: coarse stage of my query slice; the probe rows land in every group member's window ----
+        int32_t *probes = reinterpret_cast<int32_t *>(mine + L.probes);
+        const int64_t q0 = std::min<int64_t>(gq, (int64_t)s * sl), n0 = std::min<int64_t>(gq, q0 + sl) - q0;
+        {
+            StageMark sm(ix, st, 0);
+            PeerSink ps{};
+            ps.mode = 2;
+            ps.fields = SINK_IIDS;
+            ps.off_iids = (long long)L.probes;
+            for (int t = 0; t < S; ++t)
+                if (t != s) ps.base[ps.npeer++] = gb[t];
+            const int64_t QC = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / ((size_t)ix->p.nlist * sizeof(double))));
+            for (int64_t b0 = 0; b0 < n0; b0 += QC) {
+                const int64_t nb = std::min(QC, n0 - b0);
+                ps.q0 = q0 + b0;
+                Scratch sc0(st, ix->arenas, ix->arena_mu);
+                RET(coarse_probe_dev(ix, dQ + (q0 + b0) * d, nb, w, probes + (q0 + b0) * w, sc0, st, launches, &ps));
+            }
+            RET(sync(0, false));
+        }
+        // ---- stage 1: scan the lists stored here for ALL group queries; row of query q -> window of shard q / sl ----
+        PeerSink pr{};
+        pr.mode = 1;
+        pr.npeer = S;
+        pr.sl = (int)sl;
+        pr.fields = SINK_IIDS | SINK_DIST | SINK_SEQ | SINK_CNT | SINK_TIE;
+        pr.row0 = (long long)s * sl;
+        pr.off_iids = (long long)L.p_iids;
+        pr.off_dist = (long long)L.p_dist;
+        pr.off_seq = (long long)L.p_seq;
+        pr.off_cnt = (long long)L.p_cnt;
+        pr.off_tie = (long long)L.p_tie;
+        for (int t = 0; t < S; ++t) pr.base[t] = gb[t];
+        RET(search_dev_impl(ix, gq, dQ, k, nullptr, nullptr, nullptr, nullptr, nullptr, st, true, probes, &pr, false, launches));
+        StageMark sm3(ix, st, 3);
+        RET(sync(1, false));
+        // ---- merge my slice (one queue for all probed lists, IVFPQ.java:409,445) ----
+        const int64_t nslice = std::max<int64_t>(0, std::min<int64_t>(gq, q0 + sl) - q0);
+        int32_t *amb_list, *amb_count;
+        RET(sc.get(&amb_list, (size_t)sl));
+        RET(sc.get(&amb_count, 1));
+        CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+        if (nslice > 0) {
+            TopkOut part{};
+            part.iids = reinterpret_cast<int32_t *>(mine + L.p_iids);
+            part.dist = reinterpret_cast<double *>(mine + L.p_dist);
+            part.seq = reinterpret_cast<unsigned long long *>(mine + L.p_seq);
+            part.cnt = reinterpret_cast<int32_t *>(mine + L.p_cnt);
+            part.tie = reinterpret_cast<double *>(mine + L.p_tie);
+            ResultBufs res{o_iids, o_dist, nullptr, o_cnt};
+            res.sink = fin;
+            if (cap_for(k) == 2048)
+                RET(launch_merge<2048>(part, S, nslice, k, res, amb_list, amb_count, nullptr, sl, 1, st, launches));
+            else
+                RET(launch_merge<1024>(part, S, nslice, k, res, amb_list, amb_count, nullptr, sl, 1, st, launches));
+        }
+        // ---- stages 2 + 3: exact ties cut at the k-th boundary (normally none: the kernels below find empty lists) ----
+        AmbPublish ap{};
+        ap.amb_list = amb_list;
+        ap.amb_count = amb_count;
+        ap.res_dist = o_dist;
+        for (int t = 0; t < S; ++t) ap.base[t] = gb[t];
+        ap.off_cnt = (long long)L.a_cnt;
+        ap.off_q = (long long)L.a_q;
+        ap.off_T = (long long)L.a_T;
+        ap.S = S;
+        ap.shard = s;
+        ap.sl = (int)sl;
+        ap.k = k;
+        k_comm_publish_ties<<<1, MMIDX_NT, 0, st>>>(ap);
+        RET(post_launch("k_comm_publish_ties", launches));
+        RET(sync(2, false));
+        TieMultiArgs tm{};
+        tm.t.Q = dQ;
+        tm.t.C = ix->dC.as<double>();
+        tm.t.P = ix->dP.as<double>();
+        tm.t.perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
+        tm.t.probes = probes;
+        tm.t.codes = ix->csr_codes.as<uint8_t>();
+        tm.t.iids = ix->csr_iids.as<int32_t>();
+        tm.t.list_off = ix->dlist_off.as<int64_t>();
+        tm.t.list_len = ix->dlist_len.as<int32_t>();
+        tm.t.d = d;
+        tm.t.m = ix->p.m;
+        tm.t.ks = ix->p.ks;
+        tm.t.S = ix->S;
+        tm.t.w = w;
+        tm.t.k = k;
+        tm.t.code_bytes = ix->code_bytes;
+        tm.t.flat = 0;
+        tm.a_cnt = reinterpret_cast<const int32_t *>(mine + L.a_cnt);
+        tm.a_q = reinterpret_cast<const int32_t *>(mine + L.a_q);
+        tm.a_T = reinterpret_cast<const double *>(mine + L.a_T);
+        for (int t = 0; t < S; ++t) tm.base[t] = gb[t];
+        tm.off_seq = (long long)L.t_seq;
+        tm.off_pay = (long long)L.t_pay;
+        tm.off_eq = (long long)L.t_eq;
+        tm.off_cnt = (long long)L.t_cnt;
+        tm.S = S;
+        tm.shard = s;
+        tm.sl = (int)sl;
+        k_tie_collect_multi<<<ix->sm_count, MMIDX_NT, 0, st>>>(tm);
+        RET(post_launch("k_tie_collect_multi", launches));
+        RET(sync(3, false));
+        RET(set_smem(k_tie_finish, (size_t)1024 * 16));
+        k_tie_finish<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(nslice, 2 * ix->sm_count)), MMIDX_NT, (size_t)k * 16, st>>>(
+            S, sl, k, reinterpret_cast<const unsigned long long *>(mine + L.t_seq), reinterpret_cast<const int32_t *>(mine + L.t_pay),
+            reinterpret_cast<const int32_t *>(mine + L.t_eq), reinterpret_cast<const int32_t *>(mine + L.t_cnt), amb_list, amb_count,
+            o_iids, o_dist, nullptr, fin);
+        RET(post_launch("k_tie_finish", launches));
+    }
+    if (gather && c.world > 1) {
+        StageMark sm3(ix, st, 3);
+        RET(sync(4, true));
+    }
+    return MMIDX_OK;
+}
+
+static int multi_validate(mmidx_index *ix, int64_t gq, int k, int *w_out) {
+    Comm *c = ix->comm;
+    if (!c || !c->attached) return fail(MMIDX_ERR_STATE, "no attached communicator: mmidx_comm_create + mmidx_comm_attach first");
+    RET(validate_search(ix, gq, k, w_out));
+    if (gq < 1 || gq > c->max_gq) return fail(MMIDX_ERR_INVALID, "gq = %lld outside 1..%lld (the window was sized by mmidx_comm_create)", (long long)gq, (long long)c->max_gq);
+    if (k > c->k_max) return fail(MMIDX_ERR_INVALID, "k = %d exceeds the window's k_max = %d", k, c->k_max);
+    if (*w_out > c->w_max) return fail(MMIDX_ERR_UNSUPPORTED, "w = %d exceeds %d", *w_out, c->w_max);
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_search_multi_dev(mmidx_t *ix, int64_t gq, const double *dQ, int32_t k, int32_t gather_all,
+                                      const int32_t **d_iids, const double **d_dist, const int32_t **d_count, int64_t *row0,
+                                      int64_t *nrows, void *stream) {
+    if (!ix || !dQ) return fail(MMIDX_ERR_INVALID, "null argument");
+    DeviceGuard g(ix->device);
+    int w = 0;
+    RET(multi_validate(ix, gq, k, &w));
+    RET(prepare_search(ix, k));
+    Comm &c = *ix->comm;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int par = (int)(c.calls & 1);
+    GraphKey key{1, gq, k, w, gather_all ? 1 : 0, dQ, nullptr, nullptr, nullptr, st};
+    RET(run_graphed(ix, key, par, st, [&](int *launches) { return multi_enqueue(ix, gq, dQ, k, w, gather_all != 0, par, st, launches); }));
+    c.calls++;
+    const int64_t sl = (gq + c.S - 1) / c.S, gqp = sl * c.S;
+    unsigned char *mine = c.win + c.L.data0 + (size_t)par * c.L.parity_stride;
+    if (d_iids) *d_iids = reinterpret_cast<const int32_t *>(mine + c.L.o_iids);
+    if (d_dist) *d_dist = reinterpret_cast<const double *>(mine + c.L.o_dist);
+    if (d_count) *d_count = reinterpret_cast<const int32_t *>(mine + c.L.o_cnt);
+    const int64_t q0 = std::min<int64_t>(gq, (int64_t)c.shard * sl);
+    if (row0) *row0 = (int64_t)c.group * gqp + (c.S > 1 ? (int64_t)c.shard * sl : 0);
+    if (nrows) *nrows = c.S > 1 ? std::max<int64_t>(0, std::min<int64_t>(gq, q0 + sl) - q0) : gq;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_search_multi(mmidx_t *ix, int64_t gq, const double *Q, int32_t k, int32_t *out_iids, double *out_dist,
+                                  int32_t *out_count, int64_t *first_query, int64_t *nrows) {
+    if (!ix || !Q || !out_iids || !out_dist) return fail(MMIDX_ERR_INVALID, "null argument");
+    DeviceGuard g(ix->device);
+    int w = 0;
+    RET(multi_validate(ix, gq, k, &w));
+    cudaStream_t st = ix->stream;
+    Scratch sc(st, ix->arenas, ix->arena_mu);
+    double *dQ;
+    RET(sc.get(&dQ, (size_t)gq * ix->p.d));
+    CK(cudaMemcpyAsync(dQ, Q, sizeof(double) * (size_t)gq * ix->p.d, cudaMemcpyHostToDevice, st));
+    const int32_t *di;
+    const double *dd;
+    const int32_t *dc;
+    int64_t r0 = 0, nr = 0;
+    RET(mmidx_search_multi_dev(ix, gq, dQ, k, 0, &di, &dd, &dc, &r0, &nr, st));
+    if (nr > 0) {
+        CK(cudaMemcpyAsync(out_iids, di + r0 * k, sizeof(int32_t) * (size_t)nr * k, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_dist, dd + r0 * k, sizeof(double) * (size_t)nr * k, cudaMemcpyDeviceToHost, st));
+        if (out_count) CK(cudaMemcpyAsync(out_count, dc + r0, sizeof(int32_t) * (size_t)nr, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    Comm &c = *ix->comm;
+    const int64_t sl = (gq + c.S - 1) / c.S;
+    if (first_query) *first_query = c.S > 1 ? std::min<int64_t>(gq, (int64_t)c.shard * sl) : 0;
+    if (nrows) *nrows = nr;
     return MMIDX_OK;
 }
 

@@ -14,6 +14,7 @@
 // latest eq-entries (k_tie_finish).  Only queries the collectors flagged ambiguous take this path.
 #pragma once
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace mmidx {
 
@@ -184,7 +185,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_tie_finish(int nparts, int64_t nq,
                                                          const int32_t *__restrict__ l_pay, const int32_t *__restrict__ l_eq,
                                                          const int32_t *__restrict__ l_cnt, const int32_t *__restrict__ amb_list,
                                                          const int32_t *__restrict__ amb_count, int32_t *__restrict__ res_iids,
-                                                         double *__restrict__ res_dist, unsigned long long *__restrict__ res_seq) {
+                                                         double *__restrict__ res_dist, unsigned long long *__restrict__ res_seq,
+                                                         PeerSink sink) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *a_seq = reinterpret_cast<unsigned long long *>(smem_raw);  // [k] first-k le by seq
     int32_t *a_pay = reinterpret_cast<int32_t *>(a_seq + k);                       // [k]
@@ -254,6 +256,17 @@ __global__ void __launch_bounds__(MMIDX_NT) k_tie_finish(int nparts, int64_t nq,
             run += total;
         }
         __syncthreads();
+        if (sink.mode == 2) {  // multi-GPU: the patched row replaces the copy every peer already holds
+            int p0, p1;
+            const long long row = sink_dest(sink, q, p0, p1);
+            PeerSink ps = sink;
+            ps.fields &= (SINK_IIDS | SINK_DIST);
+            const int32_t *ri = res_iids + q * k;
+            const double *rd = res_dist + q * k;
+            sink_row(ps, p0, p1, row, k, k, -1.0, [=](int i) { return ri[i]; }, [=](int i) { return rd[i]; },
+                     [](int) { return 0ull; });
+            __syncthreads();
+        }
     }
 }
 

@@ -1,5 +1,7 @@
-"""Multi-GPU parity (needs >= 2 B200: gpurun --gpus 2): IVF lists sharded over 2 ranks, NCCL all-gather of the
-per-shard top-k, device merge, and the sharded tie pass -- against the unsharded CPU oracle."""
+"""Multi-GPU parity (needs >= 2 B200: gpurun --gpus 2): the whole step inside libmmidx (mmidx_search_multi_dev) --
+IVF lists sharded over the ranks, result rows stored straight into the peers' exchange windows over NVLink, epoch-flag
+exchange points, device merge and the cross-shard ordered tie pass -- against the UNSHARDED CPU oracle
+(the reference keeps one queue for all probed lists, IVFPQ.java:409,445)."""
 import os
 import socket
 
@@ -18,6 +20,37 @@ def _free_port():
     return p
 
 
+def _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather, steps=1):
+    """Q: the JOB-wide batch, split evenly over the R groups (every rank of a job steps with the same gq, so the last
+    group's batch is padded with copies of query 0).  Compares with the unsharded oracle."""
+    import torch.distributed as dist
+    nq = Q.shape[0]
+    per = (nq + mi.R - 1) // mi.R
+    g0 = mi.group * per
+    Qg = np.concatenate([Q[g0:g0 + per], np.repeat(Q[:1], max(0, g0 + per - nq), axis=0)])[:per]
+    dQ = torch.from_numpy(np.ascontiguousarray(Qg)).cuda()
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=8)
+    gqp = ((per + mi.S - 1) // mi.S) * mi.S
+    ok = True
+    for _ in range(steps):  # several steps: window parity, epochs, CUDA-graph capture on the third
+        iids, dd, cnt, row0, nrows = mi.search(k, dQ, gather_all=gather)
+        torch.cuda.synchronize()
+        if gather:
+            spans = [(g * gqp, g * per, min(nq, (g + 1) * per)) for g in range(mi.R)]
+        else:  # only this rank's rows are defined
+            a0 = g0 + (row0 - mi.group * gqp)
+            spans = [(row0, a0, min(nq, a0 + nrows))]
+        for r0, a0, a1 in spans:
+            if a1 <= a0:
+                continue
+            ok &= bool((iids[r0:r0 + a1 - a0].cpu().numpy() == oi[a0:a1]).all())
+            ok &= bool((dd[r0:r0 + a1 - a0].cpu().numpy() == od[a0:a1]).all())
+            ok &= bool((cnt[r0:r0 + a1 - a0].cpu().numpy() == oc[a0:a1]).all())
+        dist.barrier()
+    return ok
+
+
 def _worker(rank, world, port, q):
     try:
         import sys
@@ -31,55 +64,78 @@ def _worker(rank, world, port, q):
         import mmidx_b200 as M
         import pyoracle as O
         from multimedia_indexing_b200 import synth
-        from multimedia_indexing_b200.sharded import HybridIVFPQ, ShardedIVFPQ
+        from multimedia_indexing_b200.sharded import MultiIVFPQ
 
         ok = True
         msgs = []
-        for case in ("plain", "ties"):
-            d, m, ks, nlist, w, k, n, nq = 64, 8, 256, 64, 16, 100, 30000, 700
+        # ---- list sharding, S = world: plain data, then heavy duplication (exact ties cut ACROSS shards) ----
+        for case in ("plain", "ties", "exact_kernels"):
+            d, m, ks, nlist, w, k, n, nq = 64, 8, 256, 64, 16, 100, 30000, 701  # odd nq: ragged last slice
             ce = synth.mixture_centers(d, 128)
-            if case == "plain":
-                X, Q = synth.mixture(n, d, 1, ce), synth.mixture(nq, d, 2, ce)
-            else:  # heavy duplication -> exact ties at the k-th boundary across shards
+            if case == "ties":
                 base = synth.mixture(60, d, 1, ce)
                 X = base[np.random.default_rng(1).integers(0, 60, size=n)]
                 Q = base[:40] + 1.0
                 nq, k = 40, 25
+            else:
+                X, Q = synth.mixture(n, d, 1, ce), synth.mixture(nq, d, 2, ce)
+            if case == "exact_kernels":
+                ks, m = 64, 4  # outside the fused kernel's geometry: binary64 ADC-table kernels
             Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=5000, iters=3, centers=ce)
-            sh = ShardedIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist)
-            sh.loadCoarseQuantizer(Cq)
-            sh.loadProductQuantizer(P)
-            sh.setW(w)
-            # "plain": default l % G ownership; "ties": load-balanced list -> shard map (mmidx_set_shard_map)
-            lists, codes = sh.indexVectors(None, X, return_codes=True) if case == "plain" else sh.indexVectorsBalanced(X)
-            dQ = torch.from_numpy(Q).cuda()
-            iids, dd, cnt = sh.search(k, dQ)
+            mi = MultiIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist, list_shards=world)
+            mi.loadCoarseQuantizer(Cq)
+            mi.loadProductQuantizer(P)
+            mi.setW(w)
+            lists, codes = mi.indexAll(X, balanced=(case != "plain"))
+            mi.connect(max_gq=1024, k_max=128)
+            same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=4)
+            same &= _check(mi, O, synth, Cq, P, lists, codes, nlist, Q[: nq // 2], k, w, gather=False, steps=2)
+            ok &= bool(same)
+            stored = int(mi.listSizes().sum())
+            ok &= stored < n  # really sharded
+            msgs.append(f"S={world} {case}: equal={bool(same)} local_vectors={stored}")
+            # host-buffer entry point (e2e path): this rank's rows of the batch
+            hi = torch.empty((1024, k), dtype=torch.int32).pin_memory()
+            hd = torch.empty((1024, k), dtype=torch.float64).pin_memory()
+            hc = torch.empty(1024, dtype=torch.int32).pin_memory()
+            fq, nr = mi.search_host(k, np.ascontiguousarray(Q), hi, hd, hc)
             off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
             oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=8)
-            same = (iids.cpu().numpy() == oi).all() and (dd.cpu().numpy() == od).all() and (cnt.cpu().numpy() == oc).all()
-            ok &= bool(same)
-            msgs.append(f"{case}: equal={bool(same)} local_vectors={int(sh.listSizes().sum())}")
-            ok &= int(sh.listSizes().sum()) < n  # really sharded
-            sh.close()
-        # HybridIVFPQ: S list shards x R query groups; S = 1 all-gathers every group's slice in place (the layout
-        # bench.py picks for an index that fits one GPU's L2), S = world is the pure list sharding above
-        d, m, ks, nlist, w, k, n, nq = 64, 8, 256, 64, 16, 100, 30000, 1501  # odd nq: ragged last slice
+            sameh = (hi[:nr].numpy() == oi[fq:fq + nr]).all() and (hd[:nr].numpy() == od[fq:fq + nr]).all() and \
+                (hc[:nr].numpy() == oc[fq:fq + nr]).all()
+            ok &= bool(sameh)
+            msgs.append(f"S={world} {case} host path: equal={bool(sameh)} rows={nr}")
+            dist.barrier()
+            mi.close()
+        # ---- replica groups, S = 1 x R = world: every group searches its own slice, rows gathered everywhere ----
+        d, m, ks, nlist, w, k, n, nq = 64, 8, 256, 64, 16, 100, 30000, 1501
         ce = synth.mixture_centers(d, 128)
         X, Q = synth.mixture(n, d, 1, ce), synth.mixture(nq, d, 2, ce)
         Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=5000, iters=3, centers=ce)
-        for S in (1, world):
-            hy = HybridIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist, S)
-            hy.loadCoarseQuantizer(Cq)
-            hy.loadProductQuantizer(P)
-            hy.setW(w)
-            lists, codes = hy.indexAll(X)
-            iids, dd, cnt = hy.search(k, torch.from_numpy(Q).cuda())
-            off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
-            oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=8)
-            same = (iids.cpu().numpy() == oi).all() and (dd.cpu().numpy() == od).all() and (cnt.cpu().numpy() == oc).all()
+        mi = MultiIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist, list_shards=1)
+        mi.loadCoarseQuantizer(Cq)
+        mi.loadProductQuantizer(P)
+        mi.setW(w)
+        lists, codes = mi.indexAll(X)
+        mi.connect(max_gq=1024, k_max=100)
+        same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=4)
+        ok &= bool(same)
+        msgs.append(f"S=1 x R={world}: equal={bool(same)}")
+        dist.barrier()
+        mi.close()
+        if world >= 4 and world % 2 == 0:  # hybrid: 2 list shards x world/2 groups
+            mi = MultiIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist, list_shards=2)
+            mi.loadCoarseQuantizer(Cq)
+            mi.loadProductQuantizer(P)
+            mi.setW(w)
+            lists, codes = mi.indexAll(X)
+            mi.connect(max_gq=1024, k_max=100)
+            same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=4)
+            same &= _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=False, steps=2)
             ok &= bool(same)
-            msgs.append(f"hybrid S={S}: equal={bool(same)}")
-            hy.index.close()
+            msgs.append(f"S=2 x R={world // 2}: equal={bool(same)}")
+            dist.barrier()
+            mi.close()
         q.put((rank, ok, msgs))
         dist.destroy_process_group()
     except Exception as e:  # pragma: no cover
@@ -87,17 +143,58 @@ def _worker(rank, world, port, q):
         q.put((rank, False, f"{e}\n{traceback.format_exc()}"))
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_ivfpq_two_gpus():
+def _run(world):
     import torch.multiprocessing as mp
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res = [q.get(timeout=900) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] is True for r in res), res
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.timeout(1200)
+def test_multi_ivfpq_two_gpus():
+    _run(2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
+@pytest.mark.timeout(1200)
+def test_multi_ivfpq_four_gpus_hybrid():
+    """4 ranks: the S = 4 and S = 1 cases above plus the hybrid layout, 2 list shards x 2 groups"""
+    _run(4)
+
+
+@pytest.mark.timeout(600)
+def test_multi_step_on_one_gpu():
+    """world == 1 goes through the same entry points (window, epochs, graph capture) with no peers"""
+    import sys
+    import mmidx_b200 as M
+    import pyoracle as O
+    from multimedia_indexing_b200 import synth
+    from multimedia_indexing_b200.sharded import MultiIVFPQ
+
+    d, m, ks, nlist, w, k, n, nq = 32, 8, 256, 32, 8, 10, 8000, 300
+    ce = synth.mixture_centers(d, 64)
+    X, Q = synth.mixture(n, d, 1, ce), synth.mixture(nq, d, 2, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=4000, iters=3, centers=ce)
+    mi = MultiIVFPQ(d, n, m, ks, M.TransformationType.None_, nlist, list_shards=1)
+    mi.loadCoarseQuantizer(Cq)
+    mi.loadProductQuantizer(P)
+    mi.setW(w)
+    lists, codes = mi.indexAll(X)
+    mi.connect(max_gq=512, k_max=16)
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w)
+    dQ = torch.from_numpy(Q).cuda()
+    for step in range(5):
+        iids, dd, cnt, row0, nrows = mi.search(k, dQ, gather_all=True)
+        torch.cuda.synchronize()
+        assert (row0, nrows) == (0, nq)
+        assert (iids[:nq].cpu().numpy() == oi).all() and (dd[:nq].cpu().numpy() == od).all() and (cnt[:nq].cpu().numpy() == oc).all(), step
+    mi.close()

@@ -1,7 +1,8 @@
-"""World-size-2 CPU test (gloo) of the multi-GPU host logic: the list-sharding rule, the packed all-gather
-layout of multimedia_indexing_b200.sharded, and the cross-shard merge order.  Each rank plays a shard with the
-CPU oracle standing in for the kernels (tests may use the oracle), then the merged result must equal the
-unsharded oracle (the reference keeps ONE queue for all probed lists, IVFPQ.java:409,445)."""
+"""World-size-2 CPU test (gloo) of the multi-GPU host logic: the list-sharding rules and the row routing of
+multimedia_indexing_b200.sharded (the host mirror of csrc/comm.cuh: which exchange window a shard's partial queue of
+query q is stored into, and where) plus the cross-shard merge order.  Each rank plays a list shard with the CPU oracle
+standing in for the kernels (tests may use the oracle) and gloo standing in for the NVLink stores; the merged result
+must equal the unsharded oracle (the reference keeps ONE queue for all probed lists, IVFPQ.java:409,445)."""
 import os
 import socket
 
@@ -54,26 +55,57 @@ def _worker(rank, world, port, q):
             rank_of = {int(l): p for p, l in enumerate(probes[r])}
             for c in range(lc[r]):
                 seq[r, c] = (rank_of[int(lists[li[r, c]])] << 32) + pos_in_list[li[r, c]]
-        # pack exactly as ShardedIVFPQ.search_dev does and all-gather
-        offs, sizes = sharded.packed_layout(nq, k)
-        local = torch.zeros(offs[-1], dtype=torch.uint8)
-        fields = dict(iids=li, dist=ld, seq=seq, tie=np.full(nq, -1.0), cnt=lc)
-        for i, (name, dt, _) in enumerate(sharded.PACK_FIELDS):
-            raw = torch.from_numpy(np.ascontiguousarray(fields[name])).to(dt).contiguous().view(torch.uint8).view(-1)
-            local[offs[i]:offs[i] + sizes[i]] = raw
-        parts = sharded.gather_partials(local, world, nq, k)
-        # merge in BoundedPriorityQueue order: ascending distance, later-offered (larger seq) first among ties
+        # "store" every partial row into the window of the slice owner, at the row route_row() names (PeerSink ROUTE)
+        S, sl = world, sharded.slice_len(nq, world)
+        sendbuf = [torch.zeros((sl, 3 * k + 1), dtype=torch.float64) for _ in range(S)]  # iid | dist | seq | cnt
+        for qq in range(nq):
+            owner, row = sharded.route_row(qq, rank, nq, S)
+            assert row == rank * sl + (qq - owner * sl) and 0 <= owner < S
+            r = sendbuf[owner][row - rank * sl]
+            r[0:k] = torch.from_numpy(li[qq].astype(np.float64))
+            r[k:2 * k] = torch.from_numpy(ld[qq])
+            r[2 * k:3 * k] = torch.from_numpy(seq[qq].astype(np.float64))  # < 2^53: exact
+            r[3 * k] = float(lc[qq])
+        recv = [torch.zeros((sl, 3 * k + 1), dtype=torch.float64) for _ in range(S)]
+        works = [dist.isend(sendbuf[t], t) for t in range(S) if t != rank] + []
+        recv[rank] = sendbuf[rank]
+        for t in range(S):
+            if t != rank:
+                dist.recv(recv[t], t)
+        for wk in works:
+            wk.wait()
+        window = torch.cat(recv)  # [S][sl] rows: shard t's partial of slice query ql at row t*sl + ql
+        # merge my slice in BoundedPriorityQueue order: ascending distance, later-offered (larger seq) first among ties
         oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w)
         ok = True
-        for r in range(nq):
+        fin = torch.full((sl, 2 * k + 1), -1.0, dtype=torch.float64)
+        for ql in range(sl):
+            qq = rank * sl + ql
+            if qq >= nq:
+                break
             ent = []
-            for s in range(world):
-                for c in range(int(parts["cnt"][s, r])):
-                    ent.append((float(parts["dist"][s, r, c]), -int(parts["seq"][s, r, c]), int(parts["iids"][s, r, c])))
+            for t in range(S):
+                r = window[t * sl + ql]
+                for c in range(int(r[3 * k])):
+                    ent.append((float(r[k + c]), -int(r[2 * k + c]), int(r[c])))
             ent.sort()
             ent = ent[:k]
-            ok &= [e[2] for e in ent] == oi[r, :oc[r]].tolist() and [e[0] for e in ent] == od[r, :oc[r]].tolist()
-            ok &= len(ent) == oc[r]
+            ok &= [e[2] for e in ent] == oi[qq, :oc[qq]].tolist() and [e[0] for e in ent] == od[qq, :oc[qq]].tolist()
+            ok &= len(ent) == oc[qq]
+            fin[ql, :len(ent)] = torch.tensor([float(e[2]) for e in ent], dtype=torch.float64)
+            fin[ql, k:k + len(ent)] = torch.tensor([e[0] for e in ent], dtype=torch.float64)
+            fin[ql, 2 * k] = len(ent)
+        # final rows land at final_row() of the job-wide arrays on every rank (PeerSink BCAST)
+        allfin = [torch.zeros_like(fin) for _ in range(S)]
+        dist.all_gather(allfin, fin)
+        job = torch.cat(allfin)
+        for qq in range(nq):
+            row = sharded.final_row(qq, 0, nq, S)
+            n_ = int(job[row, 2 * k])
+            ok &= n_ == oc[qq] and job[row, :n_].to(torch.int64).tolist() == oi[qq, :n_].tolist()
+        # the balanced map is a valid ownership too
+        bm = sharded.balanced_shard_map(np.bincount(lists, minlength=nlist), world)
+        ok &= bm.min() >= 0 and bm.max() < world and len(bm) == nlist
         # every list is owned by exactly one rank
         owners = torch.from_numpy(own.astype(np.int32))
         dist.all_reduce(owners)
