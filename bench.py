@@ -1,21 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- queries/sec + recall@100 of IVFPQ search (BASELINE.json): 1M x 128 synthetic SIFT-shaped
-vectors, m=8, ks=256, nlist=1024, nprobe (w)=32, top-100.
+"""bench.py -- queries/sec + recall@100 of IVFPQ search (BASELINE.json).
 
-  python bench.py --gpus N --steps K --warmup W            the B200 path (libmmidx.so, through the C ABI)
-  python bench.py --impl reference --gpus N ...            the CPU arm: the oracle (C restatement of the Java
-                                                            path; the reference itself is Java and there is no JVM
-                                                            here) on all host cores, bounded query sample per step
+  python bench.py --gpus N --steps K --warmup W              the B200 path (libmmidx.so, through the C ABI)
+  python bench.py --impl reference --gpus N ...              the CPU arm: the oracle (C restatement of the Java path; the
+                                                             reference itself is Java and there is no JVM here) on all
+                                                             host cores, a bounded query sample per step
+  python bench.py --config 4 --gpus 8                        BASELINE configs[3]: 10M x 128, nlist=8192, w=64, m=16,
+                                                             list-sharded over the GPUs (database generated on device)
 
-A step = one pass of the search path over one batch of NQ queries.  `value` = device-resident queries/s
-(CUDA events on the launching stream), `e2e` = the same through the host C-ABI call mmidx_search with pinned
-HOST buffers (H2D of the queries and D2H of ids+distances inside the timed region).  N > 1: S list shards x R query
-groups (multimedia-indexing_b200/sharded.py): the lists are sharded only until one shard's codes fit half of the L2
-(S = 1 for this 12 MB index: every rank searches nq/N queries over the whole index and the results are all-gathered
-over NCCL; MMIDX_LIST_SHARDS forces list sharding with the per-shard top-k exchange and device merge).  Total work is
-fixed, so scaling is "strong"."""
+Default workload = BASELINE configs[2]: IVFPQ 1M x 128 synthetic SIFT-shaped vectors, m=8, ks=256, nlist=1024,
+nprobe (w)=32, top-100, 10 000 queries per GPU and step.  A step = one pass of the search path over one batch.
+`value` = device-resident queries/s (CUDA events on the launching stream), `e2e` = the same through the host C-ABI call
+with pinned HOST buffers (H2D of the queries and D2H of ids + distances inside the timed region).
+
+N > 1 (one process per GPU, torchrun): per-GPU work is fixed ("scaling": "weak"): every rank serves its own 10 000-query
+batch against its copy of the 12 MB index (S = 1 list shard x R = N groups) and stores its result rows into the exchange
+windows of all ranks over NVLink (multimedia-indexing_b200/csrc/comm.cuh; no NCCL call on the data path -- torch's NCCL
+group only carries the set-up handles, the per-step barrier and the max-over-ranks reduction of the timings).  The same
+line reports beside it `list_sharded` (S = N: the north_star layout, per-shard queues merged by the slice owners, same
+job batch) and `strong_scaling_10k` (10 000 queries in total, split over the ranks).
+
+Timing protocol: W >= 6 warm-up steps (the third call with a given shape is captured into a CUDA graph, once per window
+parity); every timed step is preceded by an L2 flush (256 MiB write, untimed) and, for N > 1, a barrier; K steps are timed
+per round and rounds repeat until the timed region holds >= 0.5 s; per step the MAX over ranks is taken; mean and median
+over all timed steps are reported (`value` uses the mean)."""
 import argparse
 import ctypes as C
+import importlib.util
 import json
 import os
 import subprocess
@@ -27,105 +38,74 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-
-D, M_SUB, KS, NLIST, W_PROBE, TOPK = 128, 8, 256, 1024, 32, 100
-N_DB, NQ = 1_000_000, 10_000
-NTRAIN, KM_ITERS = 50_000, 10
-N_GT = 1000  # queries with exact ground truth for recall@100
-WORKLOAD = "IVFPQ 1Mx128 nlist=1024 nprobe=32 m=8 ks=256 top-100 (BASELINE.json configs[2])"
 CACHE = os.environ.get("MMIDX_BENCH_CACHE", "/tmp/mmidx_bench_cache")
+N_GT = 1000  # queries with exact ground truth for recall@100
+MIN_TIMED_S = 0.5
+
+WL = {
+    3: dict(cfg=3, D=128, M=8, KS=256, NLIST=1024, W=32, K=100, N_DB=1_000_000, NQ=10_000, NTRAIN=100_000, ITERS=20,
+            name="IVFPQ 1Mx128 nlist=1024 nprobe=32 m=8 ks=256 top-100 (BASELINE.json configs[2])"),
+    4: dict(cfg=4, D=128, M=16, KS=256, NLIST=8192, W=64, K=100, N_DB=10_000_000, NQ=10_000, NTRAIN=262_144, ITERS=10,
+            name="IVFPQ 10Mx128 nlist=8192 nprobe=64 m=16 ks=256 top-100 (BASELINE.json configs[3])"),
+}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def load_workload(need_db=True):
-    """Deterministic inputs. Codebooks are cached on the box so both arms use the same bytes."""
-    import mmidx_b200  # noqa: F401  registers the package (loads libmmidx.so; no compute)
-    from multimedia_indexing_b200 import synth
+def load_synth():
+    """synth.py by path: the CPU arm must not load libmmidx.so"""
+    name = "mmidx_synth_standalone"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "multimedia-indexing_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
-    t0 = time.time()
-    ce = synth.mixture_centers(D)
-    key = f"d{D}_m{M_SUB}_ks{KS}_nl{NLIST}_nt{NTRAIN}_it{KM_ITERS}"
+
+def oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as O
+    return O
+
+
+def cached(path, make):
+    """npz cache on the box so both arms (and all ranks) use the same bytes"""
     os.makedirs(CACHE, exist_ok=True)
-    fq = os.path.join(CACHE, key + "_quantizers.npz")
-    if os.path.exists(fq):
-        z = np.load(fq)
-        Cq, P = z["Cq"], z["P"]
-    else:
-        Cq, P = synth.train_ivfpq(D, M_SUB, KS, NLIST, ntrain=NTRAIN, iters=KM_ITERS, centers=ce)
-        tmp = fq + f".{os.getpid()}.tmp.npz"
-        np.savez(tmp, Cq=Cq, P=P)
-        os.replace(tmp, fq)
-    X = synth.mixture(N_DB, D, synth.SEED_DB, ce) if need_db else None
-    Q = synth.mixture(NQ, D, synth.SEED_Q, ce)
-    log(f"[bench] workload ready in {time.time() - t0:.1f}s")
-    return X, Q, Cq, P, os.path.join(CACHE, key)
+    f = os.path.join(CACHE, path)
+    if os.path.exists(f):
+        z = np.load(f)
+        return {k: z[k] for k in z.files}
+    out = make()
+    tmp = f + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, **out)
+    os.replace(tmp, f)
+    return out
+
+
+def quantizers(wl, synth, centers):
+    key = f"q_d{wl['D']}_m{wl['M']}_ks{wl['KS']}_nl{wl['NLIST']}_nt{wl['NTRAIN']}_it{wl['ITERS']}.npz"
+
+    def make():
+        t0 = time.time()
+        Cq, P = synth.train_ivfpq(wl["D"], wl["M"], wl["KS"], wl["NLIST"], ntrain=wl["NTRAIN"], iters=wl["ITERS"], centers=centers)
+        log(f"[bench] trained quantizers in {time.time() - t0:.1f}s")
+        return dict(Cq=Cq, P=P)
+
+    z = cached(key, make)
+    return z["Cq"], z["P"]
+
+
+def queries_of_group(wl, synth, centers, g):
+    """group 0 searches the standard query set (SEED_Q); further groups get fresh noise from the same mixture"""
+    return synth.mixture(wl["NQ"], wl["D"], synth.SEED_Q + 7919 * g, centers)
 
 
 def recall_at_k(ids, gt):
     return float(np.mean([len(set(ids[r]) & set(gt[r])) / gt.shape[1] for r in range(gt.shape[0])]))
-
-
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
-
-
-def cpu_oracle_setup(X, Cq, P, prefix, lists=None, codes=None):
-    """CSR lists for the oracle. Encodes with the oracle itself unless assignments are given."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import pyoracle as O
-    from multimedia_indexing_b200 import synth
-
-    if lists is None:
-        f = prefix + "_oracle_codes.npz"
-        if os.path.exists(f):
-            z = np.load(f)
-            lists, codes = z["lists"], z["codes"]
-        else:
-            t0 = time.time()
-            lists, codes = O.ivfpq_encode(Cq, P, X, threads=O.num_threads())
-            codes = codes.astype(np.uint8)
-            log(f"[bench] oracle encoded {len(X)} vectors in {time.time() - t0:.1f}s on {O.num_threads()} threads")
-            tmp = f + f".{os.getpid()}.tmp.npz"
-            np.savez(tmp, lists=lists, codes=codes)
-            os.replace(tmp, f)
-    off, cc, ii = synth.csr_from_assignments(lists, np.asarray(codes, dtype=np.uint8), NLIST)
-    return O, off, cc, ii
 
 
 def exact_gt_cpu(X, Qs, k):
@@ -146,222 +126,577 @@ def exact_gt_cpu(X, Qs, k):
     return best_i
 
 
-def run_reference(args, rank):
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md); rank 0 only"""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu, enabled=True):
+        self.gpu, self.rows, self.proc, self.enabled = gpu, [], None, enabled
+
+    def start(self):
+        if not self.enabled:
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.enabled:
+            return None
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# =====================================================================================================================
+# CPU arm
+# =====================================================================================================================
+def oracle_csr(wl, synth, X, Cq, P, lists=None, codes=None):
+    O = oracle()
+    if lists is None:
+        key = f"codes_d{wl['D']}_m{wl['M']}_nl{wl['NLIST']}_n{wl['N_DB']}_nt{wl['NTRAIN']}_it{wl['ITERS']}.npz"
+
+        def make():
+            t0 = time.time()
+            l, c = O.ivfpq_encode(Cq, P, X, threads=O.num_threads())
+            log(f"[bench] oracle encoded {len(X)} vectors in {time.time() - t0:.1f}s on {O.num_threads()} threads")
+            return dict(lists=l, codes=c.astype(np.uint8))
+
+        z = cached(key, make)
+        lists, codes = z["lists"], z["codes"]
+    off, cc, ii = synth.csr_from_assignments(lists, np.asarray(codes, dtype=np.uint8), wl["NLIST"])
+    return O, off, cc, ii, lists, codes
+
+
+def cpu_rate(O, wl, Cq, P, off, cc, ii, Q, threads, seconds):
+    """queries/s of the oracle on a sample sized to take about `seconds`; returns (qps, sample, dt, result)"""
+    probe = min(len(Q), 16 * threads)
+    t0 = time.perf_counter()
+    O.ivfpq_search(Cq, P, off, cc, ii, Q[:probe], wl["K"], wl["W"], threads=threads)
+    rate = probe / (time.perf_counter() - t0)
+    sample = int(min(len(Q), max(probe, rate * seconds)))
+    t0 = time.perf_counter()
+    res = O.ivfpq_search(Cq, P, off, cc, ii, Q[:sample], wl["K"], wl["W"], threads=threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, sample, dt, res
+
+
+def run_reference(args, rank, world):
     if rank != 0:
         return
-    X, Q, Cq, P, prefix = load_workload()
-    O, off, cc, ii = cpu_oracle_setup(X, Cq, P, prefix)
+    wl = WL[args.config]
+    if wl["cfg"] == 4:
+        print(json.dumps({"impl": "reference", "unavailable": "config 4 is a GPU-only scaling run; the CPU arm is timed on the default workload"}), flush=True)
+        return
+    synth = load_synth()
+    ce = synth.mixture_centers(wl["D"])
+    Cq, P = quantizers(wl, synth, ce)
+    X = synth.mixture(wl["N_DB"], wl["D"], synth.SEED_DB, ce)
+    Q = queries_of_group(wl, synth, ce, 0)
+    O, off, cc, ii, _, _ = oracle_csr(wl, synth, X, Cq, P)
     cores = O.num_threads()
     # bounded sample per step: ~2 s of wall time on all cores
-    t0 = time.perf_counter()
-    O.ivfpq_search(Cq, P, off, cc, ii, Q[: 16 * cores], TOPK, W_PROBE, threads=cores)
-    rate = 16 * cores / (time.perf_counter() - t0)
-    sample = int(min(NQ, max(16 * cores, rate * 2.0)))
+    _, sample, _, _ = cpu_rate(O, wl, Cq, P, off, cc, ii, Q, cores, 2.0)
     for _ in range(args.warmup):
-        O.ivfpq_search(Cq, P, off, cc, ii, Q[:sample], TOPK, W_PROBE, threads=cores)
+        O.ivfpq_search(Cq, P, off, cc, ii, Q[:sample], wl["K"], wl["W"], threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ids, dist, cnt = O.ivfpq_search(Cq, P, off, cc, ii, Q[:sample], TOPK, W_PROBE, threads=cores)
+        ids, dist, cnt = O.ivfpq_search(Cq, P, off, cc, ii, Q[:sample], wl["K"], wl["W"], threads=cores)
     dt = time.perf_counter() - t0
     qps = sample * args.steps / dt
     ngt = min(sample, 200)
-    rec = recall_at_k(ids[:ngt], exact_gt_cpu(X, Q[:ngt], TOPK))
-    desc = f"first {sample} of the {NQ} queries per step, query-level threads over a shared read-only index"
+    rec = recall_at_k(ids[:ngt], exact_gt_cpu(X, Q[:ngt], wl["K"]))
+    t1_qps, t1_sample, t1_dt, _ = cpu_rate(O, wl, Cq, P, off, cc, ii, Q, 1, 3.0)
+    desc = f"first {sample} of the {wl['NQ']} queries per step, query-level threads over a shared read-only index"
     print(json.dumps({
         "impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nq_per_step": sample, "k": TOPK, "threads": cores},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "nq_per_step": wl["NQ"] * args.gpus, "k": wl["K"]},
         "recall_at_100": rec,
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": desc,
-                         "note": "C restatement of the Java path (oracle/); the Java reference cannot run here (no JVM)"},
+                         "single_thread": {"value": t1_qps, "sample": f"first {t1_sample} queries, 1 thread ({t1_dt:.1f}s): how every reference driver issues queries (Example.java:101-112)"},
+                         "note": "C restatement of the Java path (oracle/), binary heap queue, no per-offer allocation: the strongest CPU "
+                                 "form of the reference's algorithm; the Java reference itself cannot run here (no JVM)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
-def run_gpu(args, rank, world, local_rank):
-    import torch
-    import mmidx_b200 as M
-    from multimedia_indexing_b200 import _capi
+# =====================================================================================================================
+# B200 arm
+# =====================================================================================================================
+class Ctx:
+    """torch / torch.distributed plumbing of one rank"""
 
-    lib = _capi.lib
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    X, Q, Cq, P, prefix = load_workload()
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.stream = torch.cuda.current_stream()
+        self.st = C.c_void_p(self.stream.cuda_stream)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def timed(self, step, steps, warmup, after=None, wall=False, min_s=MIN_TIMED_S, max_rounds=40):
+        """The timing protocol of the module docstring.  wall: host clock around a synchronous call (e2e) instead of
+        CUDA events.  Returns per-step times in ms (max over ranks), all rounds."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        out = []
+        for _ in range(max_rounds):
+            ts = []
+            for _ in range(steps):
+                self.flush.fill_(1)  # evict L2 between timed steps (untimed)
+                self.barrier()
+                if wall:
+                    t0 = time.perf_counter()
+                    step()
+                    ts.append(1e3 * (time.perf_counter() - t0))
+                else:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(self.stream)
+                    step()
+                    b.record(self.stream)
+                    b.synchronize()
+                    ts.append(a.elapsed_time(b))
+                if after:
+                    after()
+            out.extend(self.max_over_ranks(ts).tolist())
+            if sum(out) * 1e-3 >= min_s:
+                break
+        return out
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def summarize(times_ms, queries_per_step):
+    mean, med = float(np.mean(times_ms)), float(np.median(times_ms))
+    return {"value": queries_per_step / (mean * 1e-3), "ms_per_step": mean, "median_ms_per_step": med,
+            "value_at_median": queries_per_step / (med * 1e-3), "timed_steps": len(times_ms),
+            "timed_region_s": float(np.sum(times_ms)) * 1e-3}
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in p:
+            return p["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tie_counts(ctx, M, ix, wl, Cq, dQ):
+    """How many queries have an exact binary64 tie AT the k-th (w-th) boundary: only those depend on the LingPipe tie rule
+    that the oracle restates from memory.  k+1 (w+1) results, then dist[k-1] == dist[k]."""
+    torch, lib = ctx.torch, M._capi.lib
+    nq, k, w = dQ.shape[0], wl["K"], wl["W"]
+    ii = torch.empty((nq, k + 1), dtype=torch.int32, device=ctx.dev)
+    dd = torch.empty((nq, k + 1), dtype=torch.float64, device=ctx.dev)
+    cc = torch.empty(nq, dtype=torch.int32, device=ctx.dev)
+    M._capi.check(lib.mmidx_search_dev(ix._h, nq, ptr(dQ), k + 1, ptr(ii), ptr(dd), ptr(cc), ctx.st))
+    torch.cuda.synchronize()
+    at_k = int(((dd[:, k - 1] == dd[:, k]) & (cc > k)).sum().item())
+    inside = int(((dd[:, 1:k] == dd[:, :k - 1]).any(dim=1)).sum().item())
+    # coarse stage: exact distances to the centroids = a Linear index over the centroids (same squared terms, bit for bit)
+    lin = M.Linear(wl["D"], wl["NLIST"], device=ctx.dev.index)
+    lin.indexVectors(None, Cq)
+    li = torch.empty((nq, w + 1), dtype=torch.int32, device=ctx.dev)
+    ld = torch.empty((nq, w + 1), dtype=torch.float64, device=ctx.dev)
+    lc = torch.empty(nq, dtype=torch.int32, device=ctx.dev)
+    M._capi.check(lib.mmidx_search_dev(lin._h, nq, ptr(dQ), w + 1, ptr(li), ptr(ld), ptr(lc), ctx.st))
+    torch.cuda.synchronize()
+    coarse = int((ld[:, w - 1] == ld[:, w]).sum().item())
+    lin.close()
+    return {"queries": nq, "ties_at_k_boundary": at_k, "coarse_ties_at_w_boundary": coarse,
+            "queries_with_equal_distances_inside_top_k": inside,
+            "note": "0 boundary ties => the id sets and distances of this run do not depend on any queue tie rule"}
+
+
+def small_batch(ctx, M, ix, wl, Q, cpu):
+    """latency of the reference's own call shape: a few queries per computeNearestNeighbors call
+    (AbstractSearchStructure.java:281-291), host buffers in and out through mmidx_search"""
+    torch, lib = ctx.torch, M._capi.lib
+    k = wl["K"]
+    out = {}
+    for nq, calls in ((1, 400), (32, 200), (1024, 60)):
+        hQ = torch.from_numpy(Q[:nq].copy()).pin_memory()
+        hi = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+        hd = torch.empty((nq, k), dtype=torch.float64).pin_memory()
+        hc = torch.empty(nq, dtype=torch.int32).pin_memory()
+
+        def call():
+            M._capi.check(lib.mmidx_search(ix._h, nq, ptr(hQ), k, ptr(hi), ptr(hd), ptr(hc)))
+
+        for _ in range(8):
+            call()
+        ts = []
+        for _ in range(calls):
+            t0 = time.perf_counter()
+            call()
+            ts.append(time.perf_counter() - t0)
+        med = float(np.median(ts))
+        row = {"us_per_call": 1e6 * med, "queries_per_s": nq / med, "launches_per_call": ix.lastLaunches()}
+        if cpu is not None:
+            O, Cq, P, off, cc, ii = cpu
+            for name, th in (("cpu_1_thread", 1), ("cpu_all_threads", O.num_threads())):
+                reps = 5 if nq >= 32 else 20
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q[:nq], k, wl["W"], threads=min(th, nq))
+                dt = (time.perf_counter() - t0) / reps
+                row[name] = {"us_per_call": 1e6 * dt, "queries_per_s": nq / dt}
+            row["equal_to_oracle"] = bool((hi.numpy() == oi).all() and (hd.numpy() == od).all())
+        out[str(nq)] = row
+    return out
+
+
+def other_rows(ctx, M, wl, synth, X, Q, ce, have_cpu):
+    """SURVEY 8 rows next to the headline (BASELINE configs[0], [1], [4]): device-resident timing, bounded to seconds"""
+    torch, lib = ctx.torch, M._capi.lib
+    O = oracle() if have_cpu else None
+    rows = {}
+    sm_count = torch.cuda.get_device_properties(ctx.dev).multi_processor_count
+    fp64_peak = sm_count * 64 * 1.965e9  # non-fused binary64 operations/s (64 lanes per SM), nominal
+
+    def timeit(fn, min_s=0.3):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        while sum(ts) < min_s * 1e3 and len(ts) < 400:
+            ctx.flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(ctx.stream)
+            fn()
+            b.record(ctx.stream)
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    def dev_search(ix, dQ, k):
+        nq = dQ.shape[0]
+        ii = torch.empty((nq, k), dtype=torch.int32, device=ctx.dev)
+        dd = torch.empty((nq, k), dtype=torch.float64, device=ctx.dev)
+        cc = torch.empty(nq, dtype=torch.int32, device=ctx.dev)
+        return (lambda: M._capi.check(lib.mmidx_search_dev(ix._h, nq, ptr(dQ), k, ptr(ii), ptr(dd), ptr(cc), ctx.st))), ii, dd, cc
+
+    # ---- configs[0]: Linear, 10k x 64, k = 10 ----
+    try:
+        d1, n1, k1 = 64, 10_000, 10
+        c1 = synth.mixture_centers(d1, 256)
+        X1, Q1 = synth.mixture(n1, d1, synth.SEED_DB, c1), synth.mixture(10_000, d1, synth.SEED_Q, c1)
+        lin = M.Linear(d1, n1, device=ctx.dev.index)
+        lin.indexVectors(None, X1)
+        dQ1 = torch.from_numpy(Q1).to(ctx.dev)
+        fn, ii, dd, cc = dev_search(lin, dQ1, k1)
+        ms = timeit(fn)
+        row = {"workload": "Linear 10k x 64, top-10, 10 000 queries/step (BASELINE configs[0])", "queries_per_s": 1e4 / (ms * 1e-3), "ms_per_step": ms,
+               "fp64_ops_per_s": 3.0 * n1 * d1 * 1e4 / (ms * 1e-3), "fp64_frac_of_nominal": 3.0 * n1 * d1 * 1e4 / (ms * 1e-3) / fp64_peak}
+        if O is not None:
+            ns = 1000
+            t0 = time.perf_counter()
+            oi, od, oc = O.linear_search(X1, Q1[:ns], k1, threads=O.num_threads())
+            row["cpu_queries_per_s"] = ns / (time.perf_counter() - t0)
+            row["parity_queries"] = ns
+            row["equal_to_oracle"] = bool((ii[:ns].cpu().numpy() == oi).all() and (dd[:ns].cpu().numpy() == od).all())
+        lin.close()
+        rows["linear"] = row
+    except Exception as e:  # a row never breaks the headline
+        rows["linear"] = {"error": repr(e)[:300]}
+
+    # ---- configs[1]: flat PQ over the 1M database, m = 8, top-100 ----
+    try:
+        z = cached(f"pq_d{wl['D']}_m{wl['M']}_ks{wl['KS']}.npz", lambda: dict(P=synth.train_pq(wl["D"], wl["M"], wl["KS"], ntrain=50_000, iters=10, centers=ce)))
+        Pf = z["P"]
+        pq = M.PQ(wl["D"], wl["N_DB"], wl["M"], wl["KS"], M.TransformationType.None_, device=ctx.dev.index)
+        pq.loadProductQuantizer(Pf)
+        dX = torch.from_numpy(X).to(ctx.dev)
+        dcodes = torch.empty((wl["N_DB"], wl["M"]), dtype=torch.uint8, device=ctx.dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        M._capi.check(lib.mmidx_add_dev(pq._h, wl["N_DB"], ptr(dX), None, ptr(dcodes)))
+        torch.cuda.synchronize()
+        enc_s = time.perf_counter() - t0
+        nq2 = 2000
+        dQ2 = torch.from_numpy(Q[:nq2].copy()).to(ctx.dev)
+        fn, ii, dd, cc = dev_search(pq, dQ2, wl["K"])
+        ms = timeit(fn)
+        pk, _ = peaks()
+        gbs = nq2 * wl["N_DB"] * wl["M"] / (ms * 1e-3) / 1e9
+        row = {"workload": "PQ 1Mx128 m=8 ks=256 top-100, 2000 queries/step (BASELINE configs[1])", "queries_per_s": nq2 / (ms * 1e-3), "ms_per_step": ms,
+               "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / pk, "regime": "codes L2-resident (8 MB)",
+               "pq_encode_vectors_per_s": wl["N_DB"] / enc_s,
+               "pq_encode_fp64_ops_per_s": 3.0 * wl["M"] * wl["KS"] * (wl["D"] // wl["M"]) * wl["N_DB"] / enc_s}
+        if O is not None:
+            ns = 1000
+            codes = dcodes.cpu().numpy()
+            t0 = time.perf_counter()
+            oi, od, oc = O.pq_search(Pf, codes, Q[:ns], wl["K"], threads=O.num_threads())
+            row["cpu_queries_per_s"] = ns / (time.perf_counter() - t0)
+            row["parity_queries"] = ns
+            row["equal_to_oracle"] = bool((ii[:ns].cpu().numpy() == oi).all() and (dd[:ns].cpu().numpy() == od).all())
+            ne = 20_000
+            oc2 = O.pq_encode(Pf, X[:ne], threads=O.num_threads())
+            row["codes_equal_to_oracle_first_20000"] = bool((np.asarray(oc2) == codes[:ne]).all())
+        pq.close()
+        del dX, dcodes
+        rows["pq_flat"] = row
+    except Exception as e:
+        rows["pq_flat"] = {"error": repr(e)[:300]}
+
+    # ---- configs[4]: VLAD aggregate, 100k images x ~1000 SURF(64-d) descriptors, codebook 128 ----
+    try:
+        K5, D5, chunk_img, passes = 128, 64, 2000, 50
+        desc, offs = synth.descriptors(chunk_img, D5)
+        cb = cached(f"vlad_cb_k{K5}_d{D5}.npz", lambda: dict(cb=synth.kmeans(synth.descriptors(200, D5, seed=77)[0], K5, 10, seed=5)))["cb"]
+        dcb, ddesc = torch.from_numpy(cb).to(ctx.dev), torch.from_numpy(desc).to(ctx.dev)
+        doff = torch.from_numpy(offs).to(ctx.dev)
+        dout = torch.empty((chunk_img, K5 * D5), dtype=torch.float64, device=ctx.dev)
+        dasg = torch.empty(desc.shape[0], dtype=torch.int32, device=ctx.dev)
+
+        def vlad():
+            M._capi.check(lib.mmidx_vlad_dev(ptr(dcb), K5, D5, chunk_img, ptr(doff), desc.shape[0], ptr(ddesc), ptr(dout), ptr(dasg), ctx.st))
+
+        for _ in range(2):
+            vlad()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(ctx.stream)
+        for _ in range(passes):
+            vlad()
+        b.record(ctx.stream)
+        b.synchronize()
+        s = a.elapsed_time(b) * 1e-3
+        nd = desc.shape[0] * passes
+        row = {"workload": f"VLAD K=128, {chunk_img * passes} images x ~1000 SURF-like 64-d descriptors ({passes} passes over a {chunk_img}-image chunk resident in HBM; BASELINE configs[4])",
+               "descriptors_per_s": nd / s, "images_per_s": chunk_img * passes / s, "seconds": s,
+               "fp64_ops_per_s": 3.0 * K5 * D5 * nd / s, "fp64_frac_of_nominal": 3.0 * K5 * D5 * nd / s / fp64_peak}
+        if O is not None:
+            ni = 100
+            t0 = time.perf_counter()
+            ov, oa = O.vlad(cb, desc[:offs[ni]], offs[:ni + 1], threads=O.num_threads())
+            row["cpu_descriptors_per_s"] = offs[ni] / (time.perf_counter() - t0)
+            row["parity_images"] = ni
+            row["equal_to_oracle"] = bool((dout[:ni].cpu().numpy() == ov.reshape(ni, -1)).all() and (dasg[:offs[ni]].cpu().numpy() == oa).all())
+        rows["vlad"] = row
+    except Exception as e:
+        rows["vlad"] = {"error": repr(e)[:300]}
+    return rows
+
+
+def run_gpu(args, rank, world, local_rank):
+    wl = WL[args.config]
+    ctx = Ctx(rank, world, local_rank)
+    torch = ctx.torch
+    import mmidx_b200 as M
+    from multimedia_indexing_b200 import synth
+    from multimedia_indexing_b200.sharded import MultiIVFPQ, balanced_shard_map
+
+    if wl["cfg"] == 4:
+        run_gpu_cfg4(args, ctx, M, synth, wl)
+        return
+    lib = M._capi.lib
+    NQ, K, W, D = wl["NQ"], wl["K"], wl["W"], wl["D"]
+    ce = synth.mixture_centers(D)
+    Cq, P = quantizers(wl, synth, ce)
+    X = synth.mixture(wl["N_DB"], D, synth.SEED_DB, ce)
+    G = world
+    group = rank  # main layout: S = 1, every rank is a group
+    Qg = queries_of_group(wl, synth, ce, group)
+    extras = not args.profile and not args.quick
 
     # ---- build the index (untimed): GPU coarse-assign + residual + PQ encode of the whole database ----
     t0 = time.time()
     if world > 1:
-        from multimedia_indexing_b200.sharded import HybridIVFPQ
-        # G = S list shards x R query groups (sharded.py).  Rule: shard the lists until one shard's codes + iids fit
-        # half of the 126 MB L2 (a scan that stays L2-resident), replicate beyond that.  This 12 MB index gives S = 1;
-        # BASELINE configs[3] (10M x 16 B + iids = 200 MB) gives S = 4.  MMIDX_LIST_SHARDS overrides.
-        index_bytes = N_DB * (M_SUB + 4)
-        S_auto = 1
-        while index_bytes / S_auto > 64e6 and S_auto < world:
-            S_auto *= 2
-        sh = HybridIVFPQ(D, N_DB, M_SUB, KS, M.TransformationType.None_, NLIST,
-                         int(os.environ.get("MMIDX_LIST_SHARDS", str(S_auto))))
-        ix = sh.index
+        mi = MultiIVFPQ(D, wl["N_DB"], wl["M"], wl["KS"], M.TransformationType.None_, wl["NLIST"], list_shards=1)
+        ix = mi.index
     else:
-        sh = None
-        ix = M.IVFPQ(D, N_DB, M_SUB, KS, M.TransformationType.None_, NLIST, device=local_rank)
+        mi = None
+        ix = M.IVFPQ(D, wl["N_DB"], wl["M"], wl["KS"], M.TransformationType.None_, wl["NLIST"], device=local_rank)
     ix.loadCoarseQuantizer(Cq)
     ix.loadProductQuantizer(P)
-    ix.setW(W_PROBE)
-    lists, codes = sh.indexAll(X) if sh is not None else ix.indexVectors(None, X, return_codes=True)
+    ix.setW(W)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
     log(f"[bench] rank {rank}: indexed {ix.getLoadCounter()} vectors in {time.time() - t0:.1f}s")
-    parity = {}
-    foc = prefix + "_oracle_codes.npz"
-    if rank == 0 and os.path.exists(foc):  # written by the reference arm on this box: full-size code parity
-        z = np.load(foc)
-        parity["codes_bit_exact_vs_oracle_1M"] = bool((z["lists"] == lists).all() and (z["codes"] == codes).all())
+    if mi is not None:
+        mi.connect(max_gq=NQ, k_max=K + 1)
 
-    dQ = torch.from_numpy(Q).to(dev)
-    # ---- exact ground truth for recall (measurement infrastructure, torch) ----
-    gt = None
-    if rank == 0 and not args.profile:
-        dX = torch.from_numpy(X).to(dev)
-        x2 = (dX * dX).sum(1)
-        gts = []
-        for b in range(0, N_GT, 250):
-            dd = x2[None, :] - 2.0 * (dQ[b:b + 250] @ dX.T)
-            gts.append(torch.topk(dd, TOPK, dim=1, largest=False).indices.cpu().numpy())
-        gt = np.concatenate(gts)
-        del dX, x2, dd
-        torch.cuda.empty_cache()
-
-    d_iids = torch.empty((NQ, TOPK), dtype=torch.int32, device=dev)
-    d_dist = torch.empty((NQ, TOPK), dtype=torch.float64, device=dev)
-    d_cnt = torch.empty(NQ, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-    stream = torch.cuda.current_stream()
-    st = C.c_void_p(stream.cuda_stream)
+    dQ = torch.from_numpy(Qg).to(ctx.dev)
+    d_iids = torch.empty((NQ, K), dtype=torch.int32, device=ctx.dev)
+    d_dist = torch.empty((NQ, K), dtype=torch.float64, device=ctx.dev)
+    d_cnt = torch.empty(NQ, dtype=torch.int32, device=ctx.dev)
     state = {}
 
     def step_dev():
-        if sh is None:
-            _capi.check(lib.mmidx_search_dev(ix._h, NQ, ptr(dQ), TOPK, ptr(d_iids), ptr(d_dist), ptr(d_cnt), st))
-            return d_iids, d_dist, d_cnt
-        out = sh.search(TOPK, dQ)  # includes the (normally empty) tie check, which reads 4 bytes back
-        state["res"] = out
-        return out
+        if mi is None:
+            M._capi.check(lib.mmidx_search_dev(ix._h, NQ, ptr(dQ), K, ptr(d_iids), ptr(d_dist), ptr(d_cnt), ctx.st))
+            state["res"] = (d_iids, d_dist, d_cnt)
+        else:
+            state["res"] = mi.search(K, dQ, gather_all=True)[:3]
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ----
-    nwarm = args.warmup if args.profile else max(args.warmup, 3)
-    for _ in range(nwarm):
-        step_dev()
-    torch.cuda.synchronize()
-    launches_per_step = ix.lastLaunches() + (2 if sh is not None and sh.S > 1 else 0)  # + the device merge kernels
+    # ---- device-resident timing (stage events on: they are part of what is timed) ----
+    nwarm = args.warmup if args.profile else max(args.warmup, 6)
     ix.enableTimings(True)
-    stage_ms = np.zeros(5)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
+    stage = []
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))
+    ctx.barrier()
+    clocks.start()
     wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.fill_(1)  # evict L2 between timed steps (untimed)
-        a.record(stream)
-        res = step_dev()
-        b.record(stream)
-        b.synchronize()
-        t = ix.lastTimings()
-        stage_ms += [t["coarse_ms"], t["lut_ms"], t["scan_ms"], t["merge_ms"], t["total_ms"]]
-    barrier()
+    times = ctx.timed(step_dev, args.steps, nwarm, after=lambda: stage.append(list(ix.lastTimings().values())),
+                      min_s=0.0 if args.profile else MIN_TIMED_S)
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    clk = clocks.stop()
     ix.enableTimings(False)
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    if dist is not None:
-        tt = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms = float(tt.item())
-    ms_per_step = dev_ms / args.steps
-    qps = NQ / (ms_per_step * 1e-3)
-    r_iids = res[0].cpu().numpy()
-    r_dist = res[1].cpu().numpy()
+    launches_per_step = ix.lastLaunches()
+    main = summarize(times, NQ * G)
+    stage_ms = np.mean(np.asarray(stage), axis=0)
+    res = state["res"]
+    r_iids, r_dist = res[0].cpu().numpy(), res[1].cpu().numpy()  # job-wide rows (all groups) when world > 1
 
-    if sh is not None and sh.sharded is not None and os.environ.get("MMIDX_SHARD_TIMING"):
-        log(f"[bench] rank {rank} phases ms: " + json.dumps({k: round(v, 3) for k, v in sh.sharded.last_phase_ms.items()}))
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "value": qps, "ms_per_step": ms_per_step,
-                              "stage_ms_per_step": (stage_ms / args.steps).tolist(),
-                              "gpu_launches": launches_per_step * args.steps}), flush=True)
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
+            print(json.dumps({"profile_run": True, **main, "stage_ms_per_step": stage_ms.tolist(),
+                              "gpu_launches": launches_per_step * len(times)}), flush=True)
+        ctx.close()
         return
 
-    # ---- end-to-end through the host C-ABI call, pinned host buffers ----
-    hQ = torch.from_numpy(Q).pin_memory()
-    h_iids = torch.empty((NQ, TOPK), dtype=torch.int32).pin_memory()
-    h_dist = torch.empty((NQ, TOPK), dtype=torch.float64).pin_memory()
+    # ---- end-to-end through the host C-ABI call, pinned host buffers; every rank moves its own batch ----
+    hQ = torch.from_numpy(Qg).pin_memory()
+    h_iids = torch.empty((NQ, K), dtype=torch.int32).pin_memory()
+    h_dist = torch.empty((NQ, K), dtype=torch.float64).pin_memory()
     h_cnt = torch.empty(NQ, dtype=torch.int32).pin_memory()
     h2d, d2h = hQ.numel() * 8, h_iids.numel() * 4 + h_dist.numel() * 8 + h_cnt.numel() * 4
 
     def step_e2e():
-        if sh is None:
-            _capi.check(lib.mmidx_search(ix._h, NQ, ptr(hQ), TOPK, ptr(h_iids), ptr(h_dist), ptr(h_cnt)))
-        else:
-            dq = hQ.to(dev, non_blocking=True)
-            i2, d2, c2 = sh.search(TOPK, dq)
-            if rank == 0:
-                h_iids.copy_(i2, non_blocking=True)
-                h_dist.copy_(d2, non_blocking=True)
-                h_cnt.copy_(c2, non_blocking=True)
-            torch.cuda.synchronize()
+        M._capi.check(lib.mmidx_search(ix._h, NQ, ptr(hQ), K, ptr(h_iids), ptr(h_dist), ptr(h_cnt)))
 
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)
-        barrier()
-        t0 = time.perf_counter()
-        step_e2e()
-        e2e_s += time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    e2e_qps = NQ * args.steps / e2e_s
-    if rank == 0:
-        parity["e2e_equals_device_path"] = bool((h_iids.numpy() == r_iids).all() and (h_dist.numpy() == r_dist).all())
+    e2e = summarize(ctx.timed(step_e2e, args.steps, 3, wall=True), NQ * G)
+    parity = {}
+    my_rows = slice(group * NQ, (group + 1) * NQ) if world > 1 else slice(0, NQ)
+    parity["e2e_equals_device_path"] = bool((h_iids.numpy() == r_iids[my_rows]).all() and (h_dist.numpy() == r_dist[my_rows]).all())
+
+    # ---- extra layouts on the same job batch (N > 1) ----
+    strong = sharded = None
+    if world > 1 and not args.quick:
+        # (a) strong scaling: the standard 10 000 queries in total, NQ / G per rank
+        per = (NQ + G - 1) // G
+        Q0 = queries_of_group(wl, synth, ce, 0)
+        Qs = np.concatenate([Q0, np.repeat(Q0[:1], per * G - NQ, axis=0)])[group * per:(group + 1) * per]
+        dQs = torch.from_numpy(np.ascontiguousarray(Qs)).to(ctx.dev)
+        st8 = {}
+
+        def step_strong():
+            st8["res"] = mi.search(K, dQs, gather_all=True)[:3]
+
+        strong = summarize(ctx.timed(step_strong, args.steps, 6), NQ)
+        strong["nq_per_step"] = NQ
+        s_iids, s_dist = st8["res"][0].cpu().numpy(), st8["res"][1].cpu().numpy()
+        # (b) list sharding, S = G: the north_star layout, same job batch as the headline
+        t0 = time.time()
+        ms = MultiIVFPQ(D, wl["N_DB"], wl["M"], wl["KS"], M.TransformationType.None_, wl["NLIST"], list_shards=G)
+        ms.loadCoarseQuantizer(Cq)
+        ms.loadProductQuantizer(P)
+        ms.setW(W)
+        ms.setShardMap(balanced_shard_map(np.bincount(lists, minlength=wl["NLIST"]), G))
+        ms.index.indexPQCodes(None, lists, codes)
+        ms.connect(max_gq=NQ * G, k_max=K)
+        Qall = np.concatenate([queries_of_group(wl, synth, ce, g) for g in range(G)])
+        dQall = torch.from_numpy(Qall).to(ctx.dev)
+        log(f"[bench] rank {rank}: list-sharded index ({int(ms.listSizes().sum())} of {wl['N_DB']} vectors here) in {time.time() - t0:.1f}s")
+        sh8 = {}
+
+        def step_sharded():
+            sh8["res"] = ms.search(K, dQall, gather_all=True)[:3]
+
+        ms.index.enableTimings(True)
+        sh_stage = []
+        sharded = summarize(ctx.timed(step_sharded, args.steps, 6, after=lambda: sh_stage.append(list(ms.index.lastTimings().values()))), NQ * G)
+        ms.index.enableTimings(False)
+        sharded.update(S=G, R=1, nq_per_step=NQ * G, launches_per_step=ms.index.lastLaunches(),
+                       stage_ms_per_step=dict(zip(("coarse+exchange", "prep", "scan", "merge+ties+exchange", "whole_call"), np.mean(np.asarray(sh_stage), axis=0).tolist())),
+                       vectors_on_rank0=int(ms.listSizes().sum()))
+        l_iids, l_dist = sh8["res"][0].cpu().numpy(), sh8["res"][1].cpu().numpy()
+        hQall = torch.from_numpy(Qall).pin_memory()
+        sl = (NQ * G + G - 1) // G
+        hs_i = torch.empty((sl, K), dtype=torch.int32).pin_memory()
+        hs_d = torch.empty((sl, K), dtype=torch.float64).pin_memory()
+        hs_c = torch.empty(sl, dtype=torch.int32).pin_memory()
+        sharded["e2e"] = summarize(ctx.timed(lambda: ms.search_host(K, hQall, hs_i, hs_d, hs_c), args.steps, 3, wall=True), NQ * G)
+        sharded["e2e"].update(h2d_bytes_per_step=hQall.numel() * 8, d2h_bytes_per_step=sl * K * 12 + sl * 4,
+                              note="every shard needs the whole job batch of queries; each rank reads back its slice of the results")
+        sharded["parity"] = {"equals_replica_layout_all_rows": bool((l_iids == r_iids).all() and (l_dist == r_dist).all())}
+        ms.close()
 
     if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
+        ctx.close()
         return
 
-    rec = recall_at_k(r_iids[:N_GT], gt)
-    # ---- roofline of the ADC scan kernel: algorithmic bytes = sum over probed lists of len*(m + 4) ----
-    scan_bytes = ix.scanBytes(Q) if sh is None else None
-    if sh is not None:  # this rank's share: its query group's slice, the probed lists it stores
-        q0, q1, _ = sh.slice_of(NQ)
-        probes = ix.computeNearestCoarseIndices(Q[q0:q1])
-        ls = ix.listSizes()
-        scan_bytes = int(ls[probes].sum()) * (M_SUB + 4)
-    peaks = {}
+    # ---- rank 0: parity against the oracle, recall, roofline, CPU baseline, extras ----
+    gt = None
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    scan_ms = stage_ms[2] / args.steps
+        dX = torch.from_numpy(X).to(ctx.dev)
+        x2 = (dX * dX).sum(1)
+        gts = []
+        dQ0 = torch.from_numpy(queries_of_group(wl, synth, ce, 0)[:N_GT]).to(ctx.dev)
+        for b in range(0, N_GT, 250):
+            dd = x2[None, :] - 2.0 * (dQ0[b:b + 250] @ dX.T)
+            gts.append(torch.topk(dd, K, dim=1, largest=False).indices.cpu().numpy())
+        gt = np.concatenate(gts)
+        del dX, x2, dd
+        torch.cuda.empty_cache()
+    except Exception as e:
+        log(f"[bench] ground truth failed: {e!r}")
+    rec = recall_at_k(r_iids[:N_GT], gt) if gt is not None else None
+
+    scan_bytes = ix.scanBytes(Qg)
+    peak, peak_src = peaks()
+    scan_ms = float(stage_ms[2])
     achieved = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
     traffic = None
     try:
@@ -370,79 +705,287 @@ def run_gpu(args, rank, world, local_rank):
         pass
     roof = {"bound": "hbm", "kernel": "k_ivfpq_scan_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-            "algorithmic_bytes_per_step": scan_bytes, "kernel_ms_per_step": scan_ms,
-            "note": "algorithmic bytes = sum over probed lists of len*(m+4); the 12 MB code database is L2-resident "
-                    "after first touch, the kernel is bound by shared-memory gathers + issue, see DESIGN.md 6"}
+            "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms_per_launch": scan_ms,
+            "regime": "L2-resident: the 12 MB code database stays in the 126 MB L2, so DRAM traffic (ncu, one launch on one GPU) is a few "
+                      "percent of the algorithmic bytes and the kernel's physical limits are the shared-memory pipe and issue slots; the "
+                      "HBM-streaming regime of the same kernel is profiles/r2_hbm_regime.* (DESIGN.md 6)"}
 
-    # ---- CPU baseline: the oracle on a bounded query sample, all host cores ----
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        O, off, cc, ii = cpu_oracle_setup(X, Cq, P, prefix, lists, codes)
+    O = None
+    if not args.no_cpu_baseline:
+        O, off, cc, ii, _, _ = oracle_csr(wl, synth, X, Cq, P, lists, codes)
         cores = O.num_threads()
-        t0 = time.perf_counter()
-        O.ivfpq_search(Cq, P, off, cc, ii, Q[: 16 * cores], TOPK, W_PROBE, threads=cores)
-        rate = 16 * cores / (time.perf_counter() - t0)
-        sample = int(min(NQ, max(16 * cores, rate * 12.0)))
-        t0 = time.perf_counter()
-        oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q[:sample], TOPK, W_PROBE, threads=cores)
-        dt = time.perf_counter() - t0
-        cpu = {"value": sample / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": f"first {sample} of the {NQ} queries, one pass, query-level threads ({dt:.1f}s)",
-               "recall_at_100": recall_at_k(oi[:min(sample, N_GT)], gt[:min(sample, N_GT)])}
+        qps, sample, dt, (oi, od, oc) = cpu_rate(O, wl, Cq, P, off, cc, ii, Qg, cores, 12.0 if world == 1 else 2.0)
+        cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} of the {NQ} queries of rank 0, one pass, query-level threads ({dt:.1f}s)"}
+        if gt is not None:
+            cpu["recall_at_100"] = recall_at_k(oi[:min(sample, N_GT)], gt[:min(sample, N_GT)])
+        if world == 1:
+            t1_qps, t1_sample, t1_dt, _ = cpu_rate(O, wl, Cq, P, off, cc, ii, Qg, 1, 3.0)
+            cpu["single_thread"] = {"value": t1_qps, "sample": f"first {t1_sample} queries, 1 thread ({t1_dt:.1f}s)"}
         parity["sample_queries"] = sample
         parity["ids_equal_to_oracle"] = bool((oi == r_iids[:sample]).all())
         parity["dist_bit_equal_to_oracle"] = bool((od == r_dist[:sample]).all())
         parity["max_rel_dist_err"] = float(np.max(np.abs(od - r_dist[:sample]) / np.maximum(od, 1e-300)))
-    elif world > 1 and not args.no_cpu_baseline:
-        # multi-GPU lines: the merged result of a bounded query sample against the oracle (rank 0, untimed)
-        try:
-            O, off, cc, ii = cpu_oracle_setup(X, Cq, P, prefix, lists, codes)
+        foc = os.path.join(CACHE, f"codes_d{wl['D']}_m{wl['M']}_nl{wl['NLIST']}_n{wl['N_DB']}_nt{wl['NTRAIN']}_it{wl['ITERS']}.npz")
+        if os.path.exists(foc):  # written by the reference arm on this box: full-size code parity
+            z = np.load(foc)
+            parity["codes_bit_exact_vs_oracle_1M"] = bool((z["lists"] == lists).all() and (z["codes"] == codes).all())
+        if world > 1:  # rows of the other groups (their own query sets) and the other layouts, 256 queries each
             ns = 256
-            oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q[:ns], TOPK, W_PROBE, threads=O.num_threads())
-            parity["sample_queries"] = ns
-            parity["ids_equal_to_oracle"] = bool((oi == r_iids[:ns]).all())
-            parity["dist_bit_equal_to_oracle"] = bool((od == r_dist[:ns]).all())
-        except Exception as e:  # never let the checker break a scaling line
-            parity["oracle_sample_error"] = repr(e)[:200]
+            okg = True
+            for g in range(1, G):
+                Qo = queries_of_group(wl, synth, ce, g)[:ns]
+                gi, gd, gc = O.ivfpq_search(Cq, P, off, cc, ii, Qo, K, W, threads=cores)
+                okg &= bool((gi == r_iids[g * NQ:g * NQ + ns]).all() and (gd == r_dist[g * NQ:g * NQ + ns]).all())
+            parity["other_groups_256_each_equal_to_oracle"] = okg
+            if strong is not None:
+                per = (NQ + G - 1) // G
+                Q0 = queries_of_group(wl, synth, ce, 0)
+                gi, gd, gc = O.ivfpq_search(Cq, P, off, cc, ii, Q0[:ns], K, W, threads=cores)
+                strong["parity_256_equal_to_oracle"] = bool((gi == s_iids[:ns]).all() and (gd == s_dist[:ns]).all())
+            if sharded is not None:
+                sharded["parity"]["first_256_equal_to_oracle"] = bool((oi[:ns] == l_iids[:ns]).all() and (od[:ns] == l_dist[:ns]).all())
 
     out = {
-        "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": nwarm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "metric": "queries/sec", "value": main["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": nwarm, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nq_per_step": NQ, "k": TOPK, "l2": "flushed between timed steps (256 MiB write)",
-                   "sharding": "none" if world == 1 else
-                   f"{sh.S} list shards (balanced list->shard map, per-shard top-k exchanged over NCCL, device merge) x "
-                   f"{sh.R} query groups"},
+        "config": {"workload": wl["name"], "nq_per_step": NQ * G, "k": K},
+        "layout": "1 GPU" if world == 1 else f"1 list shard x {G} groups: every rank searches its own {NQ}-query batch over its copy of the index "
+                  "and stores its rows into all ranks' exchange windows (NVLink P2P, no collective call)",
+        "l2": "flushed between timed steps (256 MiB write)",
+        "median_ms_per_step": main["median_ms_per_step"], "value_at_median": main["value_at_median"],
+        "timed_steps": main["timed_steps"], "timed_region_s": main["timed_region_s"],
+        "training": f"{wl['NTRAIN']} points, {wl['ITERS']} Lloyd iterations (SURVEY 8d)",
         "recall_at_100": rec,
-        "stage_ms_per_step": {"coarse": stage_ms[0] / args.steps, "prep": stage_ms[1] / args.steps,
-                              "scan": stage_ms[2] / args.steps, "merge_ties": stage_ms[3] / args.steps,
-                              "whole_call": stage_ms[4] / args.steps},
+        "stage_ms_per_step": dict(zip(("coarse", "prep", "scan", "merge_ties_exchange", "whole_call"), stage_ms.tolist())),
         "roofline": roof, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "mmidx_search (host pointers, pinned)"},
-        "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "parity": parity,
-        "wall_s_timed_region": wall,
+        "e2e": {"value": e2e["value"], "unit": "queries/s", "h2d_bytes_per_step": h2d * G, "d2h_bytes_per_step": d2h * G,
+                "ms_per_step": e2e["ms_per_step"], "median_ms_per_step": e2e["median_ms_per_step"], "timed_steps": e2e["timed_steps"],
+                "api": "mmidx_search (host pointers, pinned), one call per rank and step on its own batch"},
+        "gpu_launches": launches_per_step * main["timed_steps"], "launches_per_step": launches_per_step,
+        "clocks": clk, "parity": parity, "wall_s_timed_region": wall,
+    }
+    if strong is not None:
+        out["strong_scaling_10k"] = strong
+    if sharded is not None:
+        out["list_sharded"] = sharded
+    if extras:
+        t0 = time.time()
+        try:
+            out["ties"] = tie_counts(ctx, M, ix, wl, Cq, dQ)
+        except Exception as e:
+            out["ties"] = {"error": repr(e)[:300]}
+        if world == 1:
+            try:
+                out["small_batch"] = small_batch(ctx, M, ix, wl, Qg, (O, Cq, P, off, cc, ii) if O is not None else None)
+            except Exception as e:
+                out["small_batch"] = {"error": repr(e)[:300]}
+            out["rows"] = other_rows(ctx, M, wl, synth, X, Qg, ce, O is not None)
+        log(f"[bench] extras in {time.time() - t0:.1f}s")
+    print(json.dumps(out), flush=True)
+    ctx.close()
+
+
+# =====================================================================================================================
+# BASELINE configs[3]: 10M x 128, nlist = 8192, w = 64, m = 16, list-sharded across the GPUs
+# =====================================================================================================================
+def gen_on_device(torch, dev, centers_dev, n, seed, chunk=500_000):
+    """the SIFT-shaped mixture of synth.mixture, generated on the device (identical on every rank: same seeds)"""
+    for b in range(0, n, chunk):
+        nb = min(chunk, n - b)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed * 1_000_003 + b)
+        c = torch.randint(0, centers_dev.shape[0], (nb,), generator=g, device=dev)
+        x = centers_dev[c] + 20.0 * torch.randn((nb, centers_dev.shape[1]), generator=g, device=dev, dtype=torch.float64)
+        yield b, torch.clamp(torch.round(x), 0.0, 255.0)
+
+
+def kmeans_dev(torch, X, k, iters, seed):
+    g = torch.Generator(device=X.device)
+    g.manual_seed(seed)
+    C_ = X[torch.randperm(X.shape[0], generator=g, device=X.device)[:k]].clone()
+    for _ in range(iters):
+        a = torch.empty(X.shape[0], dtype=torch.int64, device=X.device)
+        c2 = (C_ * C_).sum(1)
+        for b in range(0, X.shape[0], 32768):
+            a[b:b + 32768] = torch.argmin(c2[None, :] - 2.0 * (X[b:b + 32768] @ C_.T), dim=1)
+        cnt = torch.bincount(a, minlength=k).to(X.dtype)
+        S_ = torch.zeros_like(C_).index_add_(0, a, X)
+        nz = cnt > 0
+        C_[nz] = S_[nz] / cnt[nz, None]
+    return C_
+
+
+def run_gpu_cfg4(args, ctx, M, synth, wl):
+    from multimedia_indexing_b200.sharded import MultiIVFPQ, balanced_shard_map
+    torch, lib = ctx.torch, M._capi.lib
+    rank, world = ctx.rank, ctx.world
+    NQ, K, W, D, N_DB = wl["NQ"], wl["K"], wl["W"], wl["D"], (args.n_db or wl["N_DB"])
+    ce = synth.mixture_centers(D)
+    dce = torch.from_numpy(ce).to(ctx.dev)
+
+    def make_q():
+        t0 = time.time()
+        T = torch.cat([x for _, x in gen_on_device(torch, ctx.dev, dce, wl["NTRAIN"], synth.SEED_TRAIN)])
+        Cq = kmeans_dev(torch, T, wl["NLIST"], wl["ITERS"], 11)
+        c2 = (Cq * Cq).sum(1)
+        a = torch.cat([torch.argmin(c2[None, :] - 2.0 * (T[b:b + 32768] @ Cq.T), dim=1) for b in range(0, T.shape[0], 32768)])
+        R_ = Cq[a] - T  # the reference's residual sign (IVFPQ.java:645)
+        S_ = D // wl["M"]
+        P = torch.stack([kmeans_dev(torch, R_[:, j * S_:(j + 1) * S_].contiguous(), wl["KS"], wl["ITERS"], 100 + j) for j in range(wl["M"])])
+        log(f"[bench] trained config-4 quantizers on the device in {time.time() - t0:.1f}s")
+        return dict(Cq=Cq.cpu().numpy(), P=P.cpu().numpy())
+
+    key = f"q4_d{D}_m{wl['M']}_nl{wl['NLIST']}_nt{wl['NTRAIN']}_it{wl['ITERS']}.npz"
+    if world > 1:  # rank 0 trains, everybody loads the same file
+        if rank == 0:
+            cached(key, make_q)
+        ctx.barrier()
+    z = cached(key, make_q)
+    Cq, P = z["Cq"], z["P"]
+    Q = np.concatenate([x.cpu().numpy() for _, x in gen_on_device(torch, ctx.dev, dce, NQ, synth.SEED_Q)])
+    dQ = torch.from_numpy(Q).to(ctx.dev)
+
+    def build(S):
+        t0 = time.time()
+        mi = MultiIVFPQ(D, N_DB, wl["M"], wl["KS"], M.TransformationType.None_, wl["NLIST"], list_shards=S)
+        mi.loadCoarseQuantizer(Cq)
+        mi.loadProductQuantizer(P)
+        mi.setW(W)
+        return mi, t0
+
+    # ---- replica layout (S = 1): every rank holds all 10M codes; also yields the codes for the sharded build ----
+    mi1, t0 = build(1)
+    d_lists = torch.empty(N_DB, dtype=torch.int32, device=ctx.dev)
+    d_codes = torch.empty((N_DB, wl["M"]), dtype=torch.uint8, device=ctx.dev)
+    keep_x = {}
+    for b, x in gen_on_device(torch, ctx.dev, dce, N_DB, synth.SEED_DB):
+        mi1.indexDev(x, d_lists[b:b + x.shape[0]], d_codes[b:b + x.shape[0]])
+        if b == 0:
+            keep_x[0] = x[:20_000].cpu().numpy()
+    torch.cuda.synchronize()
+    lists, codes = d_lists.cpu().numpy(), d_codes.cpu().numpy()
+    del d_lists, d_codes
+    log(f"[bench] rank {rank}: indexed {N_DB} vectors (device-generated) in {time.time() - t0:.1f}s")
+    per = (NQ + world - 1) // world
+    mi1.connect(max_gq=max(per, NQ if world == 1 else per), k_max=K)
+    results = {}
+
+    def measure(mi, dq, name, queries_per_step):
+        st = {}
+
+        def step():
+            st["res"] = mi.search(K, dq, gather_all=True)[:3]
+
+        mi.index.enableTimings(True)
+        stg = []
+        s = summarize(ctx.timed(step, args.steps, 6, after=lambda: stg.append(list(mi.index.lastTimings().values()))), queries_per_step)
+        mi.index.enableTimings(False)
+        s["stage_ms_per_step"] = dict(zip(("coarse", "prep", "scan", "merge_ties_exchange", "whole_call"), np.mean(np.asarray(stg), axis=0).tolist()))
+        s["launches_per_step"] = mi.index.lastLaunches()
+        results[name] = (s, st["res"][0].cpu().numpy(), st["res"][1].cpu().numpy())
+        return s
+
+    Qp = np.concatenate([Q, np.repeat(Q[:1], per * world - NQ, axis=0)])
+    dq1 = torch.from_numpy(np.ascontiguousarray(Qp[rank * per:(rank + 1) * per])).to(ctx.dev)
+    clocks = ClockSampler(ctx.dev.index, enabled=(rank == 0))
+    clocks.start()
+    rep = measure(mi1, dq1, "replicas", NQ)
+    rep.update(S=1, R=world)
+    scan_bytes_total = None
+    if rank == 0:
+        ls = np.bincount(lists, minlength=wl["NLIST"])
+        probes = mi1.index.computeNearestCoarseIndices(Q)
+        scan_bytes_total = int(ls[probes].sum()) * (wl["M"] + 4)
+    # ---- list sharding (S = world) ----
+    shd = None
+    if world > 1:
+        ms, t0 = build(world)
+        ms.setShardMap(balanced_shard_map(np.bincount(lists, minlength=wl["NLIST"]), world))
+        for b in range(0, N_DB, 2_000_000):  # straight through the C ABI: no host-side id map for 10M entries
+            lb, cb = np.ascontiguousarray(lists[b:b + 2_000_000]), np.ascontiguousarray(codes[b:b + 2_000_000])
+            M._capi.check(lib.mmidx_add_codes(ms.index._h, lb.shape[0], C.c_void_p(lb.ctypes.data), C.c_void_p(cb.ctypes.data)))
+        ms.connect(max_gq=NQ, k_max=K)
+        log(f"[bench] rank {rank}: list-sharded index ({int(ms.listSizes().sum())} vectors here) in {time.time() - t0:.1f}s")
+        shd = measure(ms, dQ, "sharded", NQ)
+        shd.update(S=world, R=1, vectors_on_rank0=int(ms.listSizes().sum()))
+        hQ = torch.from_numpy(Q).pin_memory()
+        sl = (NQ + world - 1) // world
+        hi, hd, hc = (torch.empty((sl, K), dtype=torch.int32).pin_memory(), torch.empty((sl, K), dtype=torch.float64).pin_memory(),
+                      torch.empty(sl, dtype=torch.int32).pin_memory())
+        e2e = summarize(ctx.timed(lambda: ms.search_host(K, hQ, hi, hd, hc), args.steps, 3, wall=True), NQ)
+        e2e.update(h2d_bytes_per_step=hQ.numel() * 8 * world, d2h_bytes_per_step=(sl * K * 12 + sl * 4) * world)
+    else:
+        hQ = torch.from_numpy(Q).pin_memory()
+        hi, hd, hc = (torch.empty((NQ, K), dtype=torch.int32).pin_memory(), torch.empty((NQ, K), dtype=torch.float64).pin_memory(),
+                      torch.empty(NQ, dtype=torch.int32).pin_memory())
+        e2e = summarize(ctx.timed(lambda: M._capi.check(lib.mmidx_search(mi1.index._h, NQ, ptr(hQ), K, ptr(hi), ptr(hd), ptr(hc))),
+                                  args.steps, 3, wall=True), NQ)
+        e2e.update(h2d_bytes_per_step=hQ.numel() * 8, d2h_bytes_per_step=NQ * K * 12 + NQ * 4)
+    clk = clocks.stop()
+    if rank != 0:
+        ctx.close()
+        return
+    head_name = "sharded" if world > 1 else "replicas"
+    head, h_iids, h_dist = results[head_name]
+    parity = {}
+    if not args.no_cpu_baseline:
+        O = oracle()
+        off, cc, ii = synth.csr_from_assignments(lists, codes, wl["NLIST"])
+        ns = 256
+        oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q[:ns], K, W, threads=O.num_threads())
+        for name, (_, ri, rd) in results.items():
+            parity[f"{name}_first_{ns}_equal_to_oracle"] = bool((ri[:ns] == oi).all() and (rd[:ns] == od).all())
+        ne = 5000
+        ol, ocodes = O.ivfpq_encode(Cq, P, keep_x[0][:ne], threads=O.num_threads())
+        parity[f"codes_first_{ne}_equal_to_oracle"] = bool((ol == lists[:ne]).all() and (np.asarray(ocodes) == codes[:ne]).all())
+    if world > 1:
+        parity["sharded_equals_replicas_all_rows"] = bool((results["sharded"][1][:NQ] == results["replicas"][1][:NQ]).all() and
+                                                          (results["sharded"][2][:NQ] == results["replicas"][2][:NQ]).all())
+    peak, peak_src = peaks()
+    scan_ms = head["stage_ms_per_step"]["scan"]
+    per_gpu_bytes = scan_bytes_total / world if world > 1 else scan_bytes_total
+    achieved = per_gpu_bytes / (scan_ms * 1e-3) / 1e9
+    out = {
+        "metric": "queries/sec", "value": head["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": 6, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (generated on the device)",
+        "config": {"workload": wl["name"] if N_DB == wl["N_DB"] else wl["name"] + f" [reduced to {N_DB} vectors]", "nq_per_step": NQ, "k": K},
+        "layout": f"{world} list shards x 1 group (per-shard queues stored into the slice owners' windows, device merge)" if world > 1 else "1 GPU",
+        "median_ms_per_step": head["median_ms_per_step"], "timed_steps": head["timed_steps"], "timed_region_s": head["timed_region_s"],
+        "stage_ms_per_step": head["stage_ms_per_step"],
+        "roofline": {"bound": "hbm", "kernel": "k_ivfpq_scan_fast<2048,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": per_gpu_bytes, "kernel_ms_per_launch": scan_ms,
+                     "note": "rank 0's launch; bytes = the job's probed-list bytes / shards (balanced map)"},
+        "list_sharded": shd, "replicas": rep,
+        "e2e": {"value": e2e["value"], "unit": "queries/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "ms_per_step": e2e["ms_per_step"]},
+        "gpu_launches": head["launches_per_step"] * head["timed_steps"], "clocks": clk, "parity": parity, "cpu_baseline": None,
     }
     print(json.dumps(out), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="3: BASELINE configs[2] (default, the metric's config); 4: configs[3]")
+    ap.add_argument("--n-db", type=int, default=0, help="config 4 only: reduced database size for quick runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only: no extra layouts, rows, latency table")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: exact warm-up count, no e2e / CPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
     else:
         run_gpu(args, rank, world, local_rank)
 

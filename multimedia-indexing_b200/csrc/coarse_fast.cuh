@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
         }
     }
     __syncthreads();
-    const int ns = s_ns;
+    // outside the fp32-safe magnitude window (fast_scan.cuh) the filter proves nothing: rank by the exact sweep below
+    const bool in_range = fast_mag_ok(qn) && fast_mag_ok(cm) && B == B && B < 1e300;
+    const int ns = in_range ? s_ns : CAP + 1;
     if (ns <= CAP) {
         // exact binary64 distance of every survivor, `vb` at a time: the block squares the terms with coalesced loads of
         // the centroid rows, then one thread per survivor adds them for j ascending -- the reference's loop

@@ -19,6 +19,11 @@ __device__ __forceinline__ double sqacc(double acc, double x, double y) {
     return __dadd_rn(acc, __dmul_rn(a, a));
 }
 
+// fp32-safe magnitude window of the fp32 filters (fast_scan.cuh, coarse_fast.cuh): a norm entering a filter is 0 or
+// inside [FAST_MAG_MIN, FAST_MAG_MAX]; FAST_ABS_SLACK is the absolute term the error radii carry for underflow.
+constexpr double FAST_MAG_MIN = 1e-12, FAST_MAG_MAX = 1e12, FAST_ABS_SLACK = 1e-30;
+__host__ __device__ inline bool fast_mag_ok(double v) { return v == 0.0 || (v >= FAST_MAG_MIN && v <= FAST_MAG_MAX); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -21,6 +21,14 @@
 // outside the result.  The collector keeps everything at or below that slack line (k entries plus the few inside
 // the error band); only those survivors (~k per query) are evaluated exactly at the end.  If the band ever holds
 // more entries than the collector can keep (massive exact duplicates) the query is handed to the direct kernel.
+//
+// fp32 range.  The bound above is relative; it holds while no fp32 intermediate overflows and while underflow errors
+// stay below the absolute slack FAST_ABS_SLACK that Bq also carries.  Both are guaranteed inside a magnitude window:
+// every norm that enters the filter (max ||C_l||, max ||P_j,c||, ||q_j||) is 0 or lies in [FAST_MAG_MIN, FAST_MAG_MAX].
+// Then no product of two components exceeds 1e24 (sums of d of them stay far below 3.4e38), and a component that
+// underflows fp32 (spacing 1.4e-45) times a factor <= 1e12, over the m(S+3) terms of a distance, errs by < 1e-30.
+// An index outside the window never takes the fast path (host check in prepare_fast); a QUERY outside the window is
+// flagged by k_fast_prep (bq = NaN) and evaluated by the table-free exact kernel.  Results are the reference's bits either way.
 #pragma once
 #include "common.cuh"
 #include "kernels.cuh"
@@ -700,8 +708,14 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
     __syncthreads();
     if (tid == 0) {
         double b = 0.0;
-        for (int j = 0; j < m; ++j) b += (double)bterm[j];
-        bq[q] = 1.02 * 5.9604644775390625e-08 * b;
+        bool ok = true;
+        for (int j = 0; j < m; ++j) {
+            b += (double)bterm[j];
+            ok = ok && fast_mag_ok((double)qn[j]);  // NaN / inf / outside the fp32-safe window -> false
+        }
+        ok = ok && b < 1e37;  // every term finite
+        // NaN marks a query the fp32 filter must not touch: the scan kernel hands it to the exact table-free kernel
+        bq[q] = ok ? 1.02 * 5.9604644775390625e-08 * b + FAST_ABS_SLACK : __longlong_as_double(0x7ff8000000000000LL);
     }
 }
 
@@ -831,7 +845,9 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     }
     for (int i = tid; i < a.d; i += MMIDX_NT) qv[i] = a.Q[q * (int64_t)a.d + i];
     __syncthreads();
-    const int nop = a.ocnt[q];
+    const double bq_q = a.bq[q];
+    const bool out_of_range = !(bq_q == bq_q);  // k_fast_prep: the query is outside the fp32-safe window
+    const int nop = out_of_range ? 0 : a.ocnt[q];
     if (tid == 0 && s < nop) {
         const int l0 = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)s * DSTRIDE)->l;
         mbar_arrive_expect_tx(&bars[0], t1_bytes);
@@ -943,7 +959,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     __syncthreads();
     if (n_before > a.k) c32.compact(a.k, a.bq[q], rel);
     const int nsurv = c32.cnt;
-    const bool overflow = c32.overflow != 0 || nsurv > ECAP;
+    const bool overflow = c32.overflow != 0 || nsurv > ECAP || out_of_range;
     TopK<ECAP> &tk = *reinterpret_cast<TopK<ECAP> *>(regA);  // aliases t2/stage/lut: no TMA is in flight any more
     int *s_l = reinterpret_cast<int *>(regA + tk_bytes);                      // [ECAP] list id of every survivor
     double *xs = reinterpret_cast<double *>(regA + tk_bytes + ECAP * sizeof(int));  // [NB][M][S + 1] squared terms

@@ -238,6 +238,8 @@ struct mmidx_index {
     std::vector<int32_t> shard_map;  // optional list -> owning shard (default l % shard_count)
     bool fast_ready = false;
     bool fast_len_ok = true;   // every list shorter than 2^22 entries (packed payload of the fp32 collector)
+    bool fast_range_ok = true;    // quantizer magnitudes inside the fp32-safe window (fast_scan.cuh); else exact kernels
+    bool coarse_range_ok = true;  // same for the fp32 coarse filter (coarse_fast.cuh)
     bool force_exact = false;  // MMIDX_MODE=exact
     bool want_stats = false;   // MMIDX_STATS=1
     size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
@@ -466,6 +468,11 @@ extern "C" int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C) {
                                                              ix->dc2.as<float>(), ix->dcmax.as<float>());
     RET(post_launch("k_coarse_tables", nullptr));
     CK(cudaStreamSynchronize(ix->stream));
+    {
+        float cm = 0.f;
+        CK(cudaMemcpy(&cm, ix->dcmax.p, sizeof(float), cudaMemcpyDeviceToHost));
+        ix->coarse_range_ok = fast_mag_ok((double)cm);  // false for inf / NaN too
+    }
     ix->has_C = true;
     ix->fast_ready = false;
     ix->gen++;
@@ -928,7 +935,7 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     // survivors evaluated per batch: up to 16 rows of squared terms, at most 32 KB (at least one row)
     const int vb = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)32 << 10) / ((size_t)(d + 1) * 8)));
     const size_t vsm = tkb + (size_t)d * 8 + (((size_t)nlist * 4 + 7) & ~(size_t)7) + (size_t)ccap * 4 + (size_t)vb * (d + 1) * 8;
-    const bool fastc = !ix->force_exact && vsm <= 160 * 1024;
+    const bool fastc = !ix->force_exact && ix->coarse_range_ok && vsm <= 160 * 1024;
     TieLists tl;
     RET(sc.get(&tl.seq, (size_t)nq * w));
     RET(sc.get(&tl.pay, (size_t)nq * w));
@@ -1342,6 +1349,16 @@ static int prepare_fast(mmidx_index *ix) {
     k_build_p32t<<<m, MMIDX_NT, 0, st>>>(P, m, ks, S, ix->dP32t.as<float>(), ix->dpmax.as<float>());
     RET(post_launch("k_build_p32t", nullptr));
     CK(cudaStreamSynchronize(st));
+    {
+        // magnitude window of the fp32 filter: max ||P_j,c||, max ||C_l|| and every T1 maximum (a squared norm)
+        std::vector<float> pm((size_t)m), tm((size_t)nlist * m);
+        CK(cudaMemcpy(pm.data(), ix->dpmax.p, sizeof(float) * pm.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(tm.data(), ix->dt1max.p, sizeof(float) * tm.size(), cudaMemcpyDeviceToHost));
+        bool ok = flat || ix->coarse_range_ok;
+        for (float v : pm) ok = ok && fast_mag_ok((double)v);
+        for (float v : tm) ok = ok && (v == 0.f || ((double)v >= FAST_MAG_MIN * FAST_MAG_MIN && (double)v <= 4.0 * FAST_MAG_MAX * FAST_MAG_MAX));
+        ix->fast_range_ok = ok;
+    }
     ix->fast_ready = true;
     return MMIDX_OK;
 }
@@ -1636,7 +1653,7 @@ static int prepare_search(mmidx_index *ix, int k) {
     const bool fast = fast_eligible(ix) && ix->fast_len_ok && k <= 256 && (ix->p.type != MMIDX_PQ || ix->flat_nlist > 0);
     if (fast && !ix->fast_ready) {
         std::lock_guard<std::mutex> lk(ix->mu);
-        RET(prepare_fast(ix));
+        RET(prepare_fast(ix));  // also decides fast_range_ok
     }
     return MMIDX_OK;
 }
@@ -1650,7 +1667,8 @@ static int search_dev_impl(mmidx_index *ix, int64_t nq, const double *dQ, int k,
     if (nq == 0) return MMIDX_OK;
     RET(prepare_search(ix, k));
     // otherwise: exact ADC-table kernels
-    const bool fast = fast_eligible(ix) && ix->fast_len_ok && k <= 256 && (ix->p.type != MMIDX_PQ || ix->flat_nlist > 0);
+    const bool fast = fast_eligible(ix) && ix->fast_len_ok && ix->fast_range_ok && k <= 256 &&
+                      (ix->p.type != MMIDX_PQ || ix->flat_nlist > 0);
     if (ix->p.type == MMIDX_PQ && fast) w = ix->flat_nlist;  // every pseudo list is probed, in iid order
     int launches = 0;
     if (reset_timer) ix->timer.reset();
