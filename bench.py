@@ -310,6 +310,9 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
+MULTI_STAGES = ("coarse", "prep", "scan", "after_scan", "whole_call", "exchange_points", "merge", "tie_pass")
+
+
 def summarize(times_ms, queries_per_step):
     mean, med = float(np.mean(times_ms)), float(np.median(times_ms))
     return {"value": queries_per_step / (mean * 1e-3), "ms_per_step": mean, "median_ms_per_step": med,
@@ -656,10 +659,10 @@ def run_gpu(args, rank, world, local_rank):
 
         ms.index.enableTimings(True)
         sh_stage = []
-        sharded = summarize(ctx.timed(step_sharded, args.steps, 6, after=lambda: sh_stage.append(list(ms.index.lastTimings().values()))), NQ * G)
+        sharded = summarize(ctx.timed(step_sharded, args.steps, 6, after=lambda: sh_stage.append(list(ms.index.lastTimingsMulti().values()))), NQ * G)
         ms.index.enableTimings(False)
         sharded.update(S=G, R=1, nq_per_step=NQ * G, launches_per_step=ms.index.lastLaunches(),
-                       stage_ms_per_step=dict(zip(("coarse+exchange", "prep", "scan", "merge+ties+exchange", "whole_call"), np.mean(np.asarray(sh_stage), axis=0).tolist())),
+                       stage_ms_per_step=dict(zip(MULTI_STAGES, np.mean(np.asarray(sh_stage), axis=0).tolist())),
                        vectors_on_rank0=int(ms.listSizes().sum()))
         l_iids, l_dist = sh8["res"][0].cpu().numpy(), sh8["res"][1].cpu().numpy()
         hQall = torch.from_numpy(Qall).pin_memory()
@@ -881,9 +884,9 @@ def run_gpu_cfg4(args, ctx, M, synth, wl):
 
         mi.index.enableTimings(True)
         stg = []
-        s = summarize(ctx.timed(step, args.steps, 6, after=lambda: stg.append(list(mi.index.lastTimings().values()))), queries_per_step)
+        s = summarize(ctx.timed(step, args.steps, 6, after=lambda: stg.append(list(mi.index.lastTimingsMulti().values()))), queries_per_step)
         mi.index.enableTimings(False)
-        s["stage_ms_per_step"] = dict(zip(("coarse", "prep", "scan", "merge_ties_exchange", "whole_call"), np.mean(np.asarray(stg), axis=0).tolist()))
+        s["stage_ms_per_step"] = dict(zip(MULTI_STAGES, np.mean(np.asarray(stg), axis=0).tolist()))
         s["launches_per_step"] = mi.index.lastLaunches()
         results[name] = (s, st["res"][0].cpu().numpy(), st["res"][1].cpu().numpy())
         return s

@@ -70,6 +70,16 @@ int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C);
 /* TransformationType.RandomPermutation (PQ.java:237-241,294-298; IVFPQ.java:319-323,420-424):
  * perm[d] as produced by RandomPermutation.java:29-40; permuted[i] = v[perm[i]].  NULL clears it. */
 int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm);
+/* TransformationType (PQ.java:30-32, same ordinals) applied before product quantization: to the vector in PQ
+ * (PQ.java:237-241, 294-298), to the residual in IVFPQ (IVFPQ.java:319-323, 420-424).
+ *   MMIDX_TRANSFORM_NONE        perm, R ignored
+ *   MMIDX_TRANSFORM_ROTATION    R[d][d] row-major: transformed = v R (RandomRotation.rotate, RandomRotation.java:44-49: the 1 x d
+ *                               row vector times the matrix, products added for i ascending).  The matrix has to be SUPPLIED:
+ *                               the reference draws it with EJML's RandomMatrices.createOrthogonal (un-vendored third-party
+ *                               code), e.g. dumped once from a JVM.  Searches then run the binary64 ADC-table kernels.
+ *   MMIDX_TRANSFORM_PERMUTATION perm[d] as for mmidx_set_permutation */
+enum { MMIDX_TRANSFORM_NONE = 0, MMIDX_TRANSFORM_ROTATION = 1, MMIDX_TRANSFORM_PERMUTATION = 2 };
+int mmidx_set_transform(mmidx_t *ix, int32_t kind, const int32_t *perm, const double *R);
 /* multi-GPU: owner[nlist] = shard that stores each inverted list (default l % shard_count); every rank must be
  * given the same map, before the first vector is indexed.  NULL restores the default. */
 int mmidx_set_shard_map(mmidx_t *ix, const int32_t *owner);
@@ -180,6 +190,9 @@ int mmidx_scan_bytes(mmidx_t *ix, int64_t nq, const double *Q, int64_t *out_tota
 /* device time in ms of the stages of the most recent search call on this index (CUDA events on the
  * launching stream): [0]=coarse [1]=LUT build [2]=ADC scan+top-k [3]=merge/tie [4]=whole call. Host-syncs. */
 int mmidx_last_timings(mmidx_t *ix, float *out5);
+/* same for a multi-GPU step, finer: [0..4] as above ([3] = everything after the scan), [5]=exchange points (flag stores
+ * + waiting for the peers, i.e. their skew), [6]=merge of the per-shard queues, [7]=cross-shard tie pass kernels */
+int mmidx_last_timings_multi(mmidx_t *ix, float *out8);
 /* record CUDA events around the stages of later search calls (off by default; not thread-safe) */
 int mmidx_enable_timings(mmidx_t *ix, int32_t on);
 /* number of kernels the most recent call launched */
@@ -197,6 +210,29 @@ int mmidx_vlad(const double *codebook, int32_t K, int32_t D, int64_t n_img, cons
                const double *desc, double *out, int32_t *out_assign, int32_t device);
 int mmidx_vlad_dev(const double *d_codebook, int32_t K, int32_t D, int64_t n_img, const int64_t *d_offsets,
                    int64_t n_desc, const double *d_desc, double *d_out, int32_t *d_assign, void *stream);
+
+/* ---- the steps around the VLAD path, batched on the device ----
+ * Normalization.normalizePower (signum(x) * pow(|x|, a), Normalization.java:74-79; a = 0.5 uses the correctly rounded
+ * square root) and / or normalizeL2 (Normalization.java:21-37: squares added for i ascending, zero norm -> all ones) applied
+ * to every row of X[rows][len] in place. */
+int mmidx_normalize_rows(double *X, int64_t rows, int64_t len, int32_t do_power, double a, int32_t do_l2, int32_t device);
+int mmidx_normalize_rows_dev(double *dX, int64_t rows, int64_t ld, int32_t len, int32_t do_power, double a, int32_t do_l2,
+                             void *stream);
+/* VladAggregatorMultipleVocabularies.aggregate (VladAggregatorMultipleVocabularies.java:84-101): nvoc codebooks stacked in
+ * codebooks[sum Ks][D]; every vocabulary aggregates the same descriptors; normalize != 0: power(0.5) + L2 per sub-VLAD and,
+ * for nvoc > 1, L2 of the concatenation.  out[n_img][sum_v Ks[v] * D]. */
+int mmidx_vlad_multi(const double *codebooks, int32_t nvoc, const int32_t *Ks, int32_t D, int64_t n_img, const int64_t *offsets,
+                     const double *desc, int32_t normalize, double *out, int32_t device);
+int mmidx_vlad_multi_dev(const double *d_codebooks, int32_t nvoc, const int32_t *Ks /* host */, int32_t D, int64_t n_img,
+                         const int64_t *d_offsets, int64_t n_desc, const double *d_desc, int32_t normalize, double *d_out,
+                         void *stream);
+/* PCA.sampleToEigenSpace (PCA.java:188-208) for n vectors: out[i] = V_t (X[i] - means), V_t[nc][ss] (for whitening the
+ * caller passes diag(eigenvalue^-0.5) V_t, as PCA.loadPCAFromFile builds it, and l2_normalize = 1).  Products are added for j
+ * ascending; EJML's own order is un-vendored, so parity with the Java path is claimed at 1e-4 relative. */
+int mmidx_pca_project(const double *Vt, const double *means, int32_t nc, int32_t ss, int64_t n, const double *X,
+                      int32_t l2_normalize, double *out, int32_t device);
+int mmidx_pca_project_dev(const double *d_Vt, const double *d_means, int32_t nc, int32_t ss, int64_t n, const double *dX,
+                          int32_t l2_normalize, double *d_out, void *stream);
 
 /* thread-local message of the last failing call on this thread */
 const char *mmidx_last_error(void);

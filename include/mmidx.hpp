@@ -75,9 +75,11 @@ public:
     long getIndexSearchTime() const { return indexSearchTime_; }
 };
 
-// reads the reference's CSV codebooks: one centroid per line, comma separated, lines without a comma skipped
-// (AbstractFeatureAggregator.readQuantizer AFA.java:234-254; PQ.loadProductQuantizer PQ.java:210-223)
-inline std::vector<double> read_csv_rows(const std::string &file, size_t rows, size_t cols) {
+// reads the reference's CSV codebooks: one centroid per line, comma separated.  skip_headers: lines without a comma are
+// skipped (AbstractFeatureAggregator.readQuantizer AFA.java:234-254: coarse quantizer, VLAD codebook); the product
+// quantizer is read line by line with no skipping (PQ.loadProductQuantizer PQ.java:210-223, IVFPQ.java:275-292), which
+// matters when subVectorLength == 1 and no line holds a comma.
+inline std::vector<double> read_csv_rows(const std::string &file, size_t rows, size_t cols, bool skip_headers = true) {
     std::ifstream in(file);
     if (!in) throw Exception(MMIDX_ERR_INVALID, "cannot open " + file);
     std::vector<double> out;
@@ -85,7 +87,7 @@ inline std::vector<double> read_csv_rows(const std::string &file, size_t rows, s
     std::string line;
     size_t got = 0;
     while (got < rows && std::getline(in, line)) {
-        if (line.find(',') == std::string::npos) continue;
+        if (skip_headers && line.find(',') == std::string::npos) continue;
         std::stringstream ss(line);
         std::string tok;
         size_t c = 0;
@@ -234,7 +236,7 @@ public:
     }
     // PQ.java:210-223: m*ks lines of subVectorLength values
     void loadProductQuantizer(const std::string &filename) {
-        loadProductQuantizer(read_csv_rows(filename, (size_t)numSubVectors * numProductCentroids, (size_t)subVectorLength));
+        loadProductQuantizer(read_csv_rows(filename, (size_t)numSubVectors * numProductCentroids, (size_t)subVectorLength, false));
     }
     void loadProductQuantizer(const std::vector<double> &P /* [m][ks][subVectorLength] */) {
         if (P.size() != (size_t)numSubVectors * numProductCentroids * subVectorLength)

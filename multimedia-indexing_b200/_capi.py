@@ -51,6 +51,7 @@ _SIGS = {
     "mmidx_set_product_quantizer": [_vp, _vp],
     "mmidx_set_coarse_quantizer": [_vp, _vp],
     "mmidx_set_permutation": [_vp, _vp],
+    "mmidx_set_transform": [_vp, _i32, _vp, _vp],
     "mmidx_set_w": [_vp, _i32],
     "mmidx_set_shard_map": [_vp, _vp],
     "mmidx_add": [_vp, _i64, _vp, _vp, _vp],
@@ -77,11 +78,18 @@ _SIGS = {
     "mmidx_get_vector": [_vp, _i64, _vp],
     "mmidx_scan_bytes": [_vp, _i64, _vp, C.POINTER(_i64)],
     "mmidx_last_timings": [_vp, _vp],
+    "mmidx_last_timings_multi": [_vp, _vp],
     "mmidx_enable_timings": [_vp, _i32],
     "mmidx_last_launches": [_vp, C.POINTER(_i32)],
     "mmidx_debug_stats": [_vp, _vp],
     "mmidx_vlad": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32],
     "mmidx_vlad_dev": [_vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
+    "mmidx_normalize_rows": [_vp, _i64, _i64, _i32, C.c_double, _i32, _i32],
+    "mmidx_normalize_rows_dev": [_vp, _i64, _i64, _i32, _i32, C.c_double, _i32, _vp],
+    "mmidx_vlad_multi": [_vp, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32],
+    "mmidx_vlad_multi_dev": [_vp, _i32, _vp, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _vp],
+    "mmidx_pca_project": [_vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _i32],
+    "mmidx_pca_project_dev": [_vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp],
 }
 for _name, _args in _SIGS.items():
     _f = getattr(lib, _name)

@@ -576,11 +576,33 @@ __global__ void __launch_bounds__(MMIDX_NT) k_merge_topk(MergeArgs a, TopkOut o)
             tk.push(pred, dv, sv, pv);
         }
     }
+    // All partial queues fit the collector uncompacted (total <= CAP: no round above compacted).  If an exact tie is cut at
+    // the k-th boundary and NO part discarded candidates at that distance, the union of the parts holds every candidate with
+    // dist <= T, so the queue's tie rule can be replayed right here (tie_resolve.cuh) -- the ordered tie pass, which
+    // re-evaluates whole lists, is left for the case where a part's own cut hides candidates.
+    __shared__ int s_amb, s_part_cut;
+    int *flag = reinterpret_cast<int *>(smem_raw + ((sizeof(TopK<CAP>) + 127) & ~(size_t)127));  // [CAP] (host sizes it)
+    __syncthreads();
+    const int nall = tk.cnt;
+    if (total <= CAP && nall > a.k) {
+        tk.sort_first(nall);
+        const bool cut = tk.dist[a.k - 1] == tk.dist[a.k];  // block-uniform
+        if (cut) {
+            if (threadIdx.x == 0) {
+                int pc = 0;
+                if (a.tie)
+                    for (int part = 0; part < a.nparts; ++part)
+                        if (a.tie[(int64_t)part * a.part_stride + q * a.q_stride] == tk.dist[a.k - 1]) pc = 1;
+                s_part_cut = pc;
+            }
+            __syncthreads();
+            if (s_part_cut == 0) tk.kill_tie_losers(nall, a.k, flag);  // losers get dist = +inf and drop out below
+        }
+    }
     bool amb;
     const int n = tk.finalize(a.k, &amb);
     // a part that discarded candidates tied at distance t makes the answer ambiguous iff t == final T
     // (T <= every part's own k-th distance, so comparing each part's value with T is exact)
-    __shared__ int s_amb;
     if (threadIdx.x == 0) {
         if (a.tie && n == a.k) {
             for (int part = 0; part < a.nparts; ++part)
@@ -807,11 +829,12 @@ __global__ void __launch_bounds__(MMIDX_NT) k_vlad_accumulate(const double *__re
                                                               const int64_t *__restrict__ offsets,
                                                               const int32_t *__restrict__ order,
                                                               const int32_t *__restrict__ cstart, int K, int D,
-                                                              double *__restrict__ out) {
+                                                              double *__restrict__ out, int64_t ld) {
+    // out rows are `ld` apart: K*D for a single vocabulary, the multi-VLAD length when several vocabularies are concatenated
     const int64_t img = blockIdx.x;
     const int64_t o0 = offsets[img];
     const int32_t *cs = cstart + img * (int64_t)(K + 1);
-    double *vo = out + img * (int64_t)K * D;
+    double *vo = out + img * ld;
     for (int e = threadIdx.x; e < K * D; e += MMIDX_NT) {
         int c = e / D, i = e - c * D;
         double cb = codebook[(int64_t)c * D + i];

@@ -28,6 +28,7 @@
 #include "coarse_fast.cuh"
 #include "fast_scan.cuh"
 #include "comm.cuh"
+#include "aux_ops.cuh"
 
 using namespace mmidx;
 
@@ -204,8 +205,8 @@ struct mmidx_index {
     mmidx_params p;
     int S = 0, code_bytes = 0, device = 0;
     int shard_rank = 0, shard_count = 1;
-    bool has_P = false, has_C = false, has_perm = false;
-    DevBuf dP, dC, dCt, dperm;
+    bool has_P = false, has_C = false, has_perm = false, has_rot = false;
+    DevBuf dP, dC, dCt, dperm, dR;  // dR: RandomRotation matrix [d][d] (mmidx_set_transform)
     int64_t n = 0;        // loadCounter: vectors offered to the index (global iid counter)
     int64_t n_local = 0;  // vectors stored on this shard
     // Linear
@@ -486,6 +487,7 @@ extern "C" int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm) {
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->fast_ready = false;
     ix->gen++;
+    ix->has_rot = false;  // TransformationType is one of None / RandomRotation / RandomPermutation (PQ.java:30-32)
     if (!perm) {
         ix->has_perm = false;
         return MMIDX_OK;
@@ -499,6 +501,29 @@ extern "C" int mmidx_set_permutation(mmidx_t *ix, const int32_t *perm) {
     CK(cudaMemcpyAsync(ix->dperm.p, perm, sizeof(int32_t) * (size_t)ix->p.d, cudaMemcpyHostToDevice, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
     ix->has_perm = true;
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_set_transform(mmidx_t *ix, int32_t kind, const int32_t *perm, const double *R) {
+    if (!ix) return fail(MMIDX_ERR_INVALID, "null argument");
+    if (ix->p.type == MMIDX_LINEAR) return fail(MMIDX_ERR_INVALID, "Linear index takes no transformation");
+    if (kind == MMIDX_TRANSFORM_NONE) return mmidx_set_permutation(ix, nullptr);
+    if (kind == MMIDX_TRANSFORM_PERMUTATION) {
+        if (!perm) return fail(MMIDX_ERR_INVALID, "RandomPermutation needs perm[d]");
+        return mmidx_set_permutation(ix, perm);
+    }
+    if (kind != MMIDX_TRANSFORM_ROTATION) return fail(MMIDX_ERR_INVALID, "unknown transformation %d", kind);
+    if (!R) return fail(MMIDX_ERR_INVALID, "RandomRotation needs the matrix R[d][d] (EJML's generator is not reproduced)");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const size_t bytes = sizeof(double) * (size_t)ix->p.d * ix->p.d;
+    RET(ix->dR.reserve(bytes, 0, ix->stream));
+    CK(cudaMemcpyAsync(ix->dR.p, R, bytes, cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    ix->has_perm = false;
+    ix->has_rot = true;
+    ix->fast_ready = false;
+    ix->gen++;
     return MMIDX_OK;
 }
 
@@ -547,11 +572,22 @@ static int launch_assign(const double *dA, const double *dBt, int64_t na, int nb
 }
 
 static int launch_pq_encode(mmidx_index *ix, const double *dX, const int32_t *dlist, int64_t n, uint8_t *dout,
-                            cudaStream_t st, int *launches) {
+                            cudaStream_t st, int *launches, Scratch &sc) {
     if (n == 0) return MMIDX_OK;
     const int S = ix->S, m = ix->p.m, ks = ix->p.ks, d = ix->p.d;
     const double *C = dlist ? ix->dC.as<double>() : nullptr;
     const int32_t *perm = ix->has_perm ? ix->dperm.as<int32_t>() : nullptr;
+    if (ix->has_rot) {
+        // RandomRotation: rotate the vector (PQ.java:237-241) / the residual (IVFPQ.java:316-323) first, then plain encode
+        double *dV;
+        RET(sc.get(&dV, (size_t)n * d));
+        k_rotate_vectors<<<(unsigned)n, MMIDX_NT, sizeof(double) * (size_t)d, st>>>(dX, C, dlist, 1, ix->dR.as<double>(), d, dV);
+        RET(post_launch("k_rotate_vectors", launches));
+        dX = dV;
+        C = nullptr;
+        dlist = nullptr;
+        perm = nullptr;
+    }
     const double *P = ix->dP.as<double>();
     dim3 grid((unsigned)((n + MMIDX_NT - 1) / MMIDX_NT), m);
     int cchunk = std::min(ks, std::max(1, (32 * 1024) / (S * 8)));
@@ -571,12 +607,12 @@ static int launch_pq_encode(mmidx_index *ix, const double *dX, const int32_t *dl
 
 // encode n device-resident vectors: dlist (IVFPQ) and dcodes receive the assignment
 static int encode_dev(mmidx_index *ix, const double *dX, int64_t n, int32_t *dlist, uint8_t *dcodes, cudaStream_t st,
-                      int *launches) {
+                      int *launches, Scratch &sc) {
     if (ix->p.type == MMIDX_IVFPQ) {
         RET(launch_assign(dX, ix->dCt.as<double>(), n, ix->p.nlist, ix->p.d, dlist, st, launches));
-        RET(launch_pq_encode(ix, dX, dlist, n, dcodes, st, launches));
+        RET(launch_pq_encode(ix, dX, dlist, n, dcodes, st, launches, sc));
     } else {
-        RET(launch_pq_encode(ix, dX, nullptr, n, dcodes, st, launches));
+        RET(launch_pq_encode(ix, dX, nullptr, n, dcodes, st, launches, sc));
     }
     return MMIDX_OK;
 }
@@ -666,7 +702,10 @@ static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *o
             CK(cudaMemcpyAsync(dX, xb, sizeof(double) * (size_t)nb * d, kin, st));
             xb = dX;
         }
-        RET(encode_dev(ix, xb, nb, dlist, dcodes, st, &launches));
+        {
+            Scratch sce(st);  // the rotated copy of a batch, when RandomRotation is set
+            RET(encode_dev(ix, xb, nb, dlist, dcodes, st, &launches, sce));
+        }
         if (out_codes) CK(cudaMemcpyAsync((uint8_t *)out_codes + b * cb, dcodes, (size_t)nb * cb, kout, st));
         if (ix->p.type == MMIDX_IVFPQ) {
             hl.resize(nb);
@@ -994,11 +1033,22 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
 static inline int64_t lut_stride_of(const mmidx_index *ix) { return ((int64_t)ix->p.m * ix->p.ks + 1) & ~(int64_t)1; }
 
 static int launch_lut(mmidx_index *ix, const double *dQ, const int32_t *dprobes, int64_t npairs, int w, double *dlut,
-                      cudaStream_t st, int *launches, bool use_perm = true) {
+                      cudaStream_t st, int *launches, Scratch &sc, bool use_transform = true) {
     if (npairs == 0) return MMIDX_OK;
     const int S = ix->S, m = ix->p.m, ks = ix->p.ks, d = ix->p.d;
-    const int32_t *perm = (use_perm && ix->has_perm) ? ix->dperm.as<int32_t>() : nullptr;
+    const int32_t *perm = (use_transform && ix->has_perm) ? ix->dperm.as<int32_t>() : nullptr;
     const double *C = dprobes ? ix->dC.as<double>() : nullptr;
+    if (use_transform && ix->has_rot) {
+        // RandomRotation of the query (PQ.java:294-298) / of every probe's residual (IVFPQ.java:417-424), then plain tables
+        double *dV;
+        RET(sc.get(&dV, (size_t)npairs * d));
+        k_rotate_vectors<<<(unsigned)npairs, MMIDX_NT, sizeof(double) * (size_t)d, st>>>(dQ, C, dprobes, w, ix->dR.as<double>(), d, dV);
+        RET(post_launch("k_rotate_vectors", launches));
+        dQ = dV;
+        C = nullptr;
+        dprobes = nullptr;
+        w = 1;
+    }
     dim3 grid((unsigned)((npairs + LUT_PT - 1) / LUT_PT), m);
     size_t smem = (size_t)LUT_PT * S * sizeof(double);
 #define LUTK(SV)                                                                                                       \
@@ -1048,7 +1098,7 @@ static int launch_merge(const TopkOut &part, int nparts, int64_t nq, int k, cons
     o.amb_list = amb_list;
     o.amb_count = amb_count;
     o.nparts = 1;
-    size_t smem = topk_bytes<CAP>();
+    size_t smem = topk_bytes<CAP>() + (size_t)CAP * sizeof(int);  // + scratch of the in-kernel tie rule
     RET(set_smem(k_merge_topk<CAP>, smem));
     k_merge_topk<CAP><<<(unsigned)nq, MMIDX_NT, smem, st>>>(a, o);
     return post_launch("k_merge_topk", launches);
@@ -1074,7 +1124,7 @@ static int ivfpq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, int
     }
     {
         StageMark sm(ix, st, 1);
-        RET(launch_lut(ix, dQ, dprobes, nq * w, w, dlut, st, launches));
+        RET(launch_lut(ix, dQ, dprobes, nq * w, w, dlut, st, launches, sc));
     }
     IvfScanArgs a{};
     a.probes = dprobes;
@@ -1165,7 +1215,7 @@ static int pq_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, const 
     RET(sc.get(&dlut, (size_t)nq * lut_stride_of(ix)));
     {
         StageMark sm(ix, st, 1);
-        RET(launch_lut(ix, dQ, nullptr, nq, 1, dlut, st, launches));
+        RET(launch_lut(ix, dQ, nullptr, nq, 1, dlut, st, launches, sc));
     }
     constexpr int ROUND = TopK<CAP>::ROUND;
     const int64_t n = ix->n_local;
@@ -1309,6 +1359,7 @@ static int linear_chunk(mmidx_index *ix, const double *dQ, int64_t nq, int k, co
 // ---------------------------------------------------------------------------------------------------------
 static bool fast_eligible(const mmidx_index *ix) {
     if (ix->force_exact) return false;
+    if (ix->has_rot) return false;  // a rotated residual goes through the binary64 ADC-table kernels
     // a flat PQ index runs the same kernels as an IVFPQ with ONE zero centroid and the negated codebook:
     // (0 - q) - (-P) = -(q - P) exactly, so every squared term has the bits of PQ.computeLookupADC (PQ.java:387-399)
     if (ix->p.type == MMIDX_PQ && ix->shard_count > 1) return false;
@@ -1978,7 +2029,7 @@ extern "C" int mmidx_tie_collect_shard_dev(mmidx_t *ix, int64_t nq, const double
         k_gather_rows<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((const uint8_t *)d_res_dist, gidx, nb, k * (int)sizeof(double), (uint8_t *)gT);
         RET(post_launch("k_gather_rows", &launches));
         RET(coarse_probe_dev(ix, gQ, nb, w, dprobes, sc, st, &launches));
-        RET(launch_lut(ix, gQ, dprobes, nb * w, w, dlut, st, &launches));
+        RET(launch_lut(ix, gQ, dprobes, nb * w, w, dlut, st, &launches, sc));
         TieLists tl;
         RET(sc.get(&tl.seq, (size_t)nb * k));
         RET(sc.get(&tl.pay, (size_t)nb * k));
@@ -2191,7 +2242,7 @@ extern "C" int mmidx_pq_lut(mmidx_t *ix, int64_t nq, const double *V, double *ou
     CK(cudaMemcpyAsync(dV, V, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
     int launches = 0;
     // computeLookupADC takes the ALREADY transformed vector (PQ.java:387): no permutation here
-    RET(launch_lut(ix, dV, nullptr, nq, 1, dl, st, &launches, false));
+    RET(launch_lut(ix, dV, nullptr, nq, 1, dl, st, &launches, sc, false));
     CK(cudaMemcpy2DAsync(out, row * sizeof(double), dl, stride * sizeof(double), row * sizeof(double), (size_t)nq,
                          cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -2256,18 +2307,21 @@ extern "C" int mmidx_scan_bytes(mmidx_t *ix, int64_t nq, const double *Q, int64_
     return MMIDX_OK;
 }
 
-extern "C" int mmidx_last_timings(mmidx_t *ix, float *out5) {
-    if (!ix || !out5) return fail(MMIDX_ERR_INVALID, "null argument");
+static int last_timings_n(mmidx_t *ix, float *out, int n) {
+    if (!ix || !out) return fail(MMIDX_ERR_INVALID, "null argument");
     DeviceGuard g(ix->device);
-    for (int i = 0; i < 5; ++i) out5[i] = 0.f;
+    for (int i = 0; i < n; ++i) out[i] = 0.f;
     for (auto &s : ix->timer.spans) {
         CK(cudaEventSynchronize(s.b));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, s.a, s.b));
-        out5[s.stage] += ms;
+        if (s.stage < n) out[s.stage] += ms;
     }
     return MMIDX_OK;
 }
+
+extern "C" int mmidx_last_timings(mmidx_t *ix, float *out5) { return last_timings_n(ix, out5, 5); }
+extern "C" int mmidx_last_timings_multi(mmidx_t *ix, float *out8) { return last_timings_n(ix, out8, 8); }
 
 extern "C" int mmidx_debug_stats(mmidx_t *ix, uint64_t *out4) {
     if (!ix || !out4) return fail(MMIDX_ERR_INVALID, "null argument");
@@ -2450,6 +2504,7 @@ static int multi_enqueue(mmidx_index *ix, int64_t gq, const double *dQ, int k, i
         }
         cs.n = n;
         if (n == 0) return MMIDX_OK;
+        StageMark smx(ix, st, 5);  // exchange point: flag stores + wait for the peers (includes their skew)
         k_comm_sync<<<1, 32, 0, st>>>(cs);
         return post_launch("k_comm_sync", launches);
     };
@@ -2519,6 +2574,7 @@ static int multi_enqueue(mmidx_index *ix, int64_t gq, const double *dQ, int k, i
         RET(sc.get(&amb_count, 1));
         CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
         if (nslice > 0) {
+            StageMark smm(ix, st, 6);
             TopkOut part{};
             part.iids = reinterpret_cast<int32_t *>(mine + L.p_iids);
             part.dist = reinterpret_cast<double *>(mine + L.p_dist);
@@ -2533,6 +2589,7 @@ static int multi_enqueue(mmidx_index *ix, int64_t gq, const double *dQ, int k, i
                 RET(launch_merge<1024>(part, S, nslice, k, res, amb_list, amb_count, nullptr, sl, 1, st, launches));
         }
         // ---- stages 2 + 3: exact ties cut at the k-th boundary (normally none: the kernels below find empty lists) ----
+        StageMark smt(ix, st, 7);  // publish + collect + finish of the cross-shard tie pass (their exchange points: stage 5)
         AmbPublish ap{};
         ap.amb_list = amb_list;
         ap.amb_count = amb_count;
@@ -2597,6 +2654,7 @@ static int multi_enqueue(mmidx_index *ix, int64_t gq, const double *dQ, int k, i
 static int multi_validate(mmidx_index *ix, int64_t gq, int k, int *w_out) {
     Comm *c = ix->comm;
     if (!c || !c->attached) return fail(MMIDX_ERR_STATE, "no attached communicator: mmidx_comm_create + mmidx_comm_attach first");
+    if (ix->has_rot) return fail(MMIDX_ERR_UNSUPPORTED, "RandomRotation is not available in the multi-GPU step (its tie pass evaluates residuals without tables)");
     RET(validate_search(ix, gq, k, w_out));
     if (gq < 1 || gq > c->max_gq) return fail(MMIDX_ERR_INVALID, "gq = %lld outside 1..%lld (the window was sized by mmidx_comm_create)", (long long)gq, (long long)c->max_gq);
     if (k > c->k_max) return fail(MMIDX_ERR_INVALID, "k = %d exceeds the window's k_max = %d", k, c->k_max);
@@ -2661,12 +2719,12 @@ extern "C" int mmidx_search_multi(mmidx_t *ix, int64_t gq, const double *Q, int3
 // ---------------------------------------------------------------------------------------------------------
 // VLAD (K7)
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int mmidx_vlad_dev(const double *d_codebook, int32_t K, int32_t D, int64_t n_img, const int64_t *d_offsets,
-                              int64_t n_desc, const double *d_desc, double *d_out, int32_t *d_assign, void *stream) {
+// one vocabulary: out rows `ld` doubles apart (the caller offsets d_out to the vocabulary's first column)
+static int vlad_dev_impl(const double *d_codebook, int32_t K, int32_t D, int64_t n_img, const int64_t *d_offsets, int64_t n_desc,
+                         const double *d_desc, double *d_out, int64_t ld, int32_t *d_assign, cudaStream_t st) {
     if (K < 1 || D < 1 || n_img < 0 || n_desc < 0) return fail(MMIDX_ERR_INVALID, "bad VLAD geometry");
     if (n_img == 0) return MMIDX_OK;
     if (!d_codebook || !d_offsets || !d_out || (n_desc > 0 && !d_desc)) return fail(MMIDX_ERR_INVALID, "null argument");
-    cudaStream_t st = (cudaStream_t)stream;
     Scratch sc(st);
     double *dBt;
     int32_t *assign = d_assign, *order, *cstart;
@@ -2684,10 +2742,182 @@ extern "C" int mmidx_vlad_dev(const double *d_codebook, int32_t K, int32_t D, in
         k_vlad_order<<<(unsigned)nb, MMIDX_NT, smem, st>>>(assign, d_offsets + i0, K, order, cstart + i0 * (K + 1));
         RET(post_launch("k_vlad_order", nullptr));
         k_vlad_accumulate<<<(unsigned)nb, MMIDX_NT, 0, st>>>(d_codebook, d_desc, d_offsets + i0, order, cstart + i0 * (K + 1), K, D,
-                                                            d_out + i0 * (int64_t)K * D);
+                                                            d_out + i0 * ld, ld);
         RET(post_launch("k_vlad_accumulate", nullptr));
     }
     return MMIDX_OK;
+}
+
+extern "C" int mmidx_vlad_dev(const double *d_codebook, int32_t K, int32_t D, int64_t n_img, const int64_t *d_offsets,
+                              int64_t n_desc, const double *d_desc, double *d_out, int32_t *d_assign, void *stream) {
+    return vlad_dev_impl(d_codebook, K, D, n_img, d_offsets, n_desc, d_desc, d_out, (int64_t)K * D, d_assign, (cudaStream_t)stream);
+}
+
+extern "C" int mmidx_normalize_rows_dev(double *dX, int64_t rows, int64_t ld, int32_t len, int32_t do_power, double a,
+                                        int32_t do_l2, void *stream) {
+    if (rows < 0 || len < 1 || ld < len) return fail(MMIDX_ERR_INVALID, "bad row geometry");
+    if (rows == 0 || (!do_power && !do_l2)) return MMIDX_OK;
+    if (!dX) return fail(MMIDX_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t r0 = 0; r0 < rows; r0 += 1 << 30) {
+        const int64_t nb = std::min<int64_t>(1 << 30, rows - r0);
+        k_rows_normalize<<<(unsigned)nb, MMIDX_NT, 0, st>>>(dX + r0 * ld, ld, len, do_power, a, do_l2);
+        RET(post_launch("k_rows_normalize", nullptr));
+    }
+    return MMIDX_OK;
+}
+
+// VladAggregatorMultipleVocabularies.aggregate (VAMV.java:84-101): every vocabulary aggregates the SAME descriptors;
+// power(0.5) + L2 per sub-VLAD, concatenation, one more L2 over the whole vector when there are several vocabularies
+extern "C" int mmidx_vlad_multi_dev(const double *d_codebooks, int32_t nvoc, const int32_t *Ks, int32_t D, int64_t n_img,
+                                    const int64_t *d_offsets, int64_t n_desc, const double *d_desc, int32_t normalize,
+                                    double *d_out, void *stream) {
+    if (nvoc < 1 || !Ks) return fail(MMIDX_ERR_INVALID, "bad vocabulary list");
+    int64_t total = 0;
+    for (int v = 0; v < nvoc; ++v) {
+        if (Ks[v] < 1) return fail(MMIDX_ERR_INVALID, "vocabulary %d has no centroids", v);
+        total += (int64_t)Ks[v] * D;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t col = 0, krow = 0;
+    for (int v = 0; v < nvoc; ++v) {
+        RET(vlad_dev_impl(d_codebooks + krow * D, Ks[v], D, n_img, d_offsets, n_desc, d_desc, d_out + col, total, nullptr, st));
+        if (normalize) RET(mmidx_normalize_rows_dev(d_out + col, n_img, total, Ks[v] * D, 1, 0.5, 1, st));
+        col += (int64_t)Ks[v] * D;
+        krow += Ks[v];
+    }
+    if (normalize && nvoc > 1) RET(mmidx_normalize_rows_dev(d_out, n_img, total, (int32_t)total, 0, 0.0, 1, st));
+    return MMIDX_OK;
+}
+
+extern "C" int mmidx_pca_project_dev(const double *d_Vt, const double *d_means, int32_t nc, int32_t ss, int64_t n,
+                                     const double *dX, int32_t l2_normalize, double *d_out, void *stream) {
+    if (nc < 1 || ss < 1 || n < 0) return fail(MMIDX_ERR_INVALID, "bad PCA geometry");
+    if (n == 0) return MMIDX_OK;
+    if (!d_Vt || !d_means || !dX || !d_out) return fail(MMIDX_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t r0 = 0; r0 < n; r0 += (int64_t)PCA_T * 65535) {
+        const int64_t nb = std::min<int64_t>((int64_t)PCA_T * 65535, n - r0);
+        dim3 grid((unsigned)((nc + PCA_T - 1) / PCA_T), (unsigned)((nb + PCA_T - 1) / PCA_T));
+        k_pca_project<<<grid, MMIDX_NT, 0, st>>>(dX + r0 * ss, d_means, d_Vt, nb, nc, ss, d_out + r0 * nc);
+        RET(post_launch("k_pca_project", nullptr));
+    }
+    if (l2_normalize) RET(mmidx_normalize_rows_dev(d_out, n, nc, nc, 0, 0.0, 1, st));  // PCA.java:203-204 (whitening)
+    return MMIDX_OK;
+}
+
+// host-buffer wrappers of the three entry points above: copy in, run, copy out, synchronise
+struct HostCall {
+    cudaStream_t st = nullptr;
+    int rc = MMIDX_OK;
+    explicit HostCall(int32_t &device) {
+        if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
+        rc = check_device(device);
+    }
+};
+
+extern "C" int mmidx_normalize_rows(double *X, int64_t rows, int64_t len, int32_t do_power, double a, int32_t do_l2, int32_t device) {
+    if (rows < 0 || len < 1 || len > INT32_MAX) return fail(MMIDX_ERR_INVALID, "bad row geometry");
+    if (rows == 0) return MMIDX_OK;
+    if (!X) return fail(MMIDX_ERR_INVALID, "null argument");
+    HostCall hc(device);
+    RET(hc.rc);
+    DeviceGuard g(device);
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch sc(st);
+        auto body = [&]() -> int {
+            double *dX;
+            RET(sc.get(&dX, (size_t)rows * len));
+            CK(cudaMemcpyAsync(dX, X, sizeof(double) * (size_t)rows * len, cudaMemcpyHostToDevice, st));
+            RET(mmidx_normalize_rows_dev(dX, rows, len, (int32_t)len, do_power, a, do_l2, st));
+            CK(cudaMemcpyAsync(X, dX, sizeof(double) * (size_t)rows * len, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            return MMIDX_OK;
+        };
+        rc = body();
+    }
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+extern "C" int mmidx_vlad_multi(const double *codebooks, int32_t nvoc, const int32_t *Ks, int32_t D, int64_t n_img,
+                                const int64_t *offsets, const double *desc, int32_t normalize, double *out, int32_t device) {
+    if (nvoc < 1 || !Ks || D < 1 || n_img < 0) return fail(MMIDX_ERR_INVALID, "bad VLAD geometry");
+    if (n_img == 0) return MMIDX_OK;
+    if (!codebooks || !offsets || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    for (int64_t i = 0; i < n_img; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(MMIDX_ERR_INVALID, "offsets must be non-decreasing");
+    if (offsets[0] != 0) return fail(MMIDX_ERR_INVALID, "offsets[0] must be 0");
+    const int64_t n_desc = offsets[n_img];
+    if (n_desc > 0 && !desc) return fail(MMIDX_ERR_INVALID, "null argument");
+    int64_t ksum = 0;
+    for (int v = 0; v < nvoc; ++v) ksum += Ks[v] > 0 ? Ks[v] : 0;
+    HostCall hc(device);
+    RET(hc.rc);
+    DeviceGuard g(device);
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch sc(st);
+        auto body = [&]() -> int {
+            double *dcb, *ddesc, *dout;
+            int64_t *doff;
+            RET(sc.get(&dcb, (size_t)ksum * D));
+            RET(sc.get(&ddesc, (size_t)std::max<int64_t>(n_desc, 1) * D));
+            RET(sc.get(&dout, (size_t)n_img * ksum * D));
+            RET(sc.get(&doff, (size_t)n_img + 1));
+            CK(cudaMemcpyAsync(dcb, codebooks, sizeof(double) * (size_t)ksum * D, cudaMemcpyHostToDevice, st));
+            if (n_desc) CK(cudaMemcpyAsync(ddesc, desc, sizeof(double) * (size_t)n_desc * D, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(doff, offsets, sizeof(int64_t) * (size_t)(n_img + 1), cudaMemcpyHostToDevice, st));
+            RET(mmidx_vlad_multi_dev(dcb, nvoc, Ks, D, n_img, doff, n_desc, ddesc, normalize, dout, st));
+            CK(cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)n_img * ksum * D, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            return MMIDX_OK;
+        };
+        rc = body();
+    }
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+extern "C" int mmidx_pca_project(const double *Vt, const double *means, int32_t nc, int32_t ss, int64_t n, const double *X,
+                                 int32_t l2_normalize, double *out, int32_t device) {
+    if (nc < 1 || ss < 1 || n < 0) return fail(MMIDX_ERR_INVALID, "bad PCA geometry");
+    if (n == 0) return MMIDX_OK;
+    if (!Vt || !means || !X || !out) return fail(MMIDX_ERR_INVALID, "null argument");
+    HostCall hc(device);
+    RET(hc.rc);
+    DeviceGuard g(device);
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch sc(st);
+        auto body = [&]() -> int {
+            double *dV, *dm, *dX, *dY;
+            RET(sc.get(&dV, (size_t)nc * ss));
+            RET(sc.get(&dm, (size_t)ss));
+            RET(sc.get(&dX, (size_t)n * ss));
+            RET(sc.get(&dY, (size_t)n * nc));
+            CK(cudaMemcpyAsync(dV, Vt, sizeof(double) * (size_t)nc * ss, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dm, means, sizeof(double) * (size_t)ss, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(dX, X, sizeof(double) * (size_t)n * ss, cudaMemcpyHostToDevice, st));
+            RET(mmidx_pca_project_dev(dV, dm, nc, ss, n, dX, l2_normalize, dY, st));
+            CK(cudaMemcpyAsync(out, dY, sizeof(double) * (size_t)n * nc, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            return MMIDX_OK;
+        };
+        rc = body();
+    }
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
 }
 
 extern "C" int mmidx_vlad(const double *codebook, int32_t K, int32_t D, int64_t n_img, const int64_t *offsets,

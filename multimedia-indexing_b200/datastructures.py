@@ -216,6 +216,12 @@ class AbstractSearchStructure:
         check(lib.mmidx_last_timings(self._h, _ptr(t)))
         return dict(zip(("coarse_ms", "lut_ms", "scan_ms", "merge_ms", "total_ms"), map(float, t)))
 
+    def lastTimingsMulti(self):
+        t = np.zeros(8, dtype=np.float32)
+        check(lib.mmidx_last_timings_multi(self._h, _ptr(t)))
+        return dict(zip(("coarse_ms", "prep_ms", "scan_ms", "after_scan_ms", "total_ms", "exchange_points_ms", "merge_ms", "tie_pass_ms"),
+                        map(float, t)))
+
     def enableTimings(self, on=True):
         check(lib.mmidx_enable_timings(self._h, 1 if on else 0))
 
@@ -272,7 +278,7 @@ class Linear(AbstractSearchStructure):
 
 
 class _PQBase(AbstractSearchStructure):
-    def _init_pq(self, numSubVectors, numProductCentroids, transformation):
+    def _init_pq(self, numSubVectors, numProductCentroids, transformation, rotation=None):
         self.numSubVectors = int(numSubVectors)
         self.numProductCentroids = int(numProductCentroids)
         self.subVectorLength = self.vectorLength // self.numSubVectors
@@ -281,8 +287,17 @@ class _PQBase(AbstractSearchStructure):
             # PQ.java:155-156: new RandomPermutation(seed = 1, vectorLength)
             self.setPermutation(random_permutation(1, self.vectorLength))
         elif transformation == TransformationType.RandomRotation:
-            # EJML's RandomMatrices.createOrthogonal is un-vendored third-party code
-            raise MmidxError(_capi.ERR_UNSUPPORTED, "RandomRotation needs EJML's matrix; not reproducible here")
+            # PQ.java:153-154: new RandomRotation(seed, vectorLength) draws the matrix with EJML's
+            # RandomMatrices.createOrthogonal -- un-vendored third-party code, so the d x d matrix has to
+            # be supplied (e.g. dumped once from a JVM); it is then applied exactly as RandomRotation.rotate does
+            if rotation is None:
+                raise MmidxError(_capi.ERR_UNSUPPORTED, "RandomRotation needs EJML's matrix: pass rotation=R[d][d]")
+            self.setRotation(rotation)
+
+    def setRotation(self, R):
+        """TransformationType.RandomRotation with a supplied matrix: transformed = v R (RandomRotation.java:44-49)"""
+        R = _f64(R, (self.vectorLength, self.vectorLength))
+        check(lib.mmidx_set_transform(self._h, 1, None, _ptr(R)))
 
     def setPermutation(self, perm):
         perm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
@@ -323,9 +338,9 @@ class PQ(_PQBase):
     _type = _capi.MMIDX_PQ
 
     def __init__(self, vectorLength, maxNumVectors, numSubVectors, numProductCentroids,
-                 transformation=TransformationType.None_, device=-1):
+                 transformation=TransformationType.None_, device=-1, rotation=None):
         super().__init__(vectorLength, maxNumVectors, m=numSubVectors, ks=numProductCentroids, device=device)
-        self._init_pq(numSubVectors, numProductCentroids, transformation)
+        self._init_pq(numSubVectors, numProductCentroids, transformation, rotation)
 
     def indexPQCodes(self, ids, codes):
         codes = np.ascontiguousarray(codes, dtype=np.uint8 if self.numProductCentroids <= 256 else np.uint16)
@@ -342,12 +357,13 @@ class IVFPQ(_PQBase):
     _type = _capi.MMIDX_IVFPQ
 
     def __init__(self, vectorLength, maxNumVectors, numSubVectors, numProductCentroids,
-                 transformation=TransformationType.None_, numCoarseCentroids=1, device=-1, shard_rank=0, shard_count=0):
+                 transformation=TransformationType.None_, numCoarseCentroids=1, device=-1, shard_rank=0, shard_count=0,
+                 rotation=None):
         super().__init__(vectorLength, maxNumVectors, m=numSubVectors, ks=numProductCentroids,
                          nlist=numCoarseCentroids, w=0, device=device, shard_rank=shard_rank, shard_count=shard_count)
         self.numCoarseCentroids = int(numCoarseCentroids)
         self.w = int(numCoarseCentroids * 0.1)  # IVFPQ.java:188
-        self._init_pq(numSubVectors, numProductCentroids, transformation)
+        self._init_pq(numSubVectors, numProductCentroids, transformation, rotation)
 
     def setW(self, w):
         """IVFPQ.java:95-97"""

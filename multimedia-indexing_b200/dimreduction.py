@@ -6,17 +6,25 @@ the VLAD vector and the index in the authors' pipeline (ImageVectorization.java:
   PCA.sampleToEigenSpace    J/dimreduction/PCA.java:188-208   y = V_t (x - mean); with whitening V_t is pre-multiplied
                                                               by diag(eigenvalue^-0.5) and y is L2-normalised
 
-Learning the basis (addSample / computeBasis, EJML SVD) is out of scope.  The projection is evaluated as the plain
-row-times-vector loop (products added for j ascending); EJML is not vendored, so whether that is its exact summation
-order is unverified -- parity is claimed within the 1e-4 relative tolerance only; the final L2 step is the bit-identical
-one of aggregation.normalizeL2.  Plain numpy: the reference runs this on the CPU as well."""
+Learning the basis (addSample / computeBasis, EJML SVD) is out of scope.  The projection runs on the device
+(mmidx_pca_project: a tiled binary64 product, the products of a row added for j ascending -- the row-times-vector loop);
+EJML is not vendored, so whether that is its exact summation order is unverified and parity with the Java path is claimed
+within the 1e-4 relative tolerance only; the final L2 step is the bit-identical one of Normalization.normalizeL2.
+The file format and the whitening fold-in are host logic, as in the reference."""
+import ctypes as C
+
 import numpy as np
 
-from .aggregation import normalizeL2
+from ._capi import check, lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
 
 
 class PCA:
-    def __init__(self, numComponents, numSamples, sampleSize, doWhitening=False):
+    def __init__(self, numComponents, numSamples, sampleSize, doWhitening=False, device=-1):
+        self.device = device
         self.numComponents, self.numSamples, self.sampleSize = int(numComponents), int(numSamples), int(sampleSize)
         self.doWhitening = bool(doWhitening)
         self.means = None
@@ -57,16 +65,13 @@ class PCA:
         X = np.asarray(X, dtype=np.float64)
         if X.ndim != 2 or X.shape[1] != self.sampleSize:
             raise ValueError("Unexpected vector length!")
-        # y_i = sum_j V_t[i][j] * (x_j - mean_j), products rounded then added for j ascending (the plain row-times-vector
-        # loop of EJML's MatrixVectorMult; np.cumsum adds sequentially) -- deterministic, and the same for one vector
-        # or a batch
-        Xc = X - self.means[None, :]
+        # y_i = sum_j V_t[i][j] * (x_j - mean_j) on the device; whitening: L2 of every projected row (PCA.java:203-205)
+        X = np.ascontiguousarray(X)
         Y = np.empty((X.shape[0], self.numComponents), dtype=np.float64)
-        step = max(1, (1 << 23) // max(1, self.numComponents * self.sampleSize))
-        for b in range(0, X.shape[0], step):
-            prod = Xc[b:b + step, None, :] * self.V_t[None, :, :]
-            Y[b:b + step] = np.cumsum(prod, axis=2)[:, :, -1]
-        return normalizeL2(Y) if self.doWhitening else Y
+        if X.shape[0]:
+            check(lib.mmidx_pca_project(_ptr(self.V_t), _ptr(self.means), self.numComponents, self.sampleSize, X.shape[0], _ptr(X),
+                                        1 if self.doWhitening else 0, _ptr(Y), self.device))
+        return Y
 
     def sampleToEigenSpace(self, sampleData):
         return self.sampleToEigenSpaceBatch(np.asarray(sampleData, dtype=np.float64).reshape(1, -1))[0]

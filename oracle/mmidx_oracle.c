@@ -163,13 +163,58 @@ int orc_pq_nearest_product_index(const double *P, int ks, int S, int sub, const 
     return best;
 }
 
+/* RandomRotation.rotate RandomRotation.java:44-49: CommonOps.mult(original[1 x d], randomMatrix[d x d], transformed):
+ * transformed[j] = sum_i v[i] * R[i][j], i ascending, product rounded then added (Java has no fused multiply-add).
+ * EJML is un-vendored third-party code: the accumulation order is the natural row-vector-times-matrix one, unverified. */
+void orc_apply_rotation(const double *R, int d, const double *v, double *out) {
+    for (int j = 0; j < d; j++) {
+        double acc = 0;
+        for (int i = 0; i < d; i++) {
+            double p = v[i] * R[(size_t)i * d + j];
+            acc += p;
+        }
+        out[j] = acc;
+    }
+}
+
+/* The transformation in force for the calls below: TransformationType is ONE of None / RandomRotation / RandomPermutation
+ * (PQ.java:30-32; `if RandomRotation ... else if RandomPermutation`, PQ.java:237-241).  A rotation is installed with
+ * orc_set_rotation (test infrastructure: a process-wide setting, not thread-safe to change during a batch call). */
+static const double *g_rot = NULL;
+static int g_rot_d = 0;
+void orc_set_rotation(const double *R, int d) {
+    g_rot = R;
+    g_rot_d = d;
+}
+
 /* RandomPermutation.permute RandomPermutation.java:50-56: permuted[i] = vector[perm[i]] */
 static void apply_perm(const int32_t *perm, const double *v, int d, double *out) {
-    if (perm) {
+    if (g_rot && g_rot_d == d) {
+        orc_apply_rotation(g_rot, d, v, out);
+    } else if (perm) {
         for (int i = 0; i < d; i++) out[i] = v[perm[i]];
     } else {
         memcpy(out, v, sizeof(double) * (size_t)d);
     }
+}
+
+/* PCA.sampleToEigenSpace PCA.java:188-208: CommonOps.sub(sample, means, sample); CommonOps.mult(V_t, sample, projected)
+ * (matrix times vector: total += V_t[i][j] * sample[j], j ascending); with whitening the result is L2-normalised
+ * (Normalization.normalizeL2).  V_t is the matrix PCA.loadPCAFromFile leaves in place (whitening folded in, :281-300). */
+void orc_normalize_l2(double *v, int64_t n);
+void orc_pca_project(const double *Vt, const double *means, int nc, int ss, const double *x, int l2, double *out) {
+    double *s = (double *)malloc(sizeof(double) * (size_t)ss);
+    for (int j = 0; j < ss; j++) s[j] = x[j] - means[j];
+    for (int i = 0; i < nc; i++) {
+        double total = 0;
+        for (int j = 0; j < ss; j++) {
+            double p = Vt[(size_t)i * ss + j] * s[j];
+            total += p;
+        }
+        out[i] = total;
+    }
+    free(s);
+    if (l2) orc_normalize_l2(out, nc);
 }
 
 /* PQ.indexVectorInternal PQ.java:232-268 (transform then per-sub-vector argmin) */

@@ -70,6 +70,12 @@ int orc_nearest_centroid(const double *codebook, int K, int D, const double *des
 void orc_vlad(const double *codebook, int K, int D, const double *desc, int64_t n, double *out /*[K*D]*/,
               int32_t *out_assign /* [n] or NULL */);
 /* Normalization.java:21-37 (L2; zero vector -> all ones) and :74-79 (signed power) */
+/* RandomRotation.rotate RandomRotation.java:44-49; orc_set_rotation installs / clears (NULL) the rotation that the
+ * encode / search functions apply instead of `perm` */
+void orc_apply_rotation(const double *R, int d, const double *v, double *out);
+void orc_set_rotation(const double *R, int d);
+/* PCA.sampleToEigenSpace PCA.java:188-208 */
+void orc_pca_project(const double *Vt, const double *means, int nc, int ss, const double *x, int l2, double *out);
 void orc_normalize_l2(double *v, int64_t n);
 void orc_normalize_power(double *v, int64_t n, double a);
 

@@ -187,3 +187,48 @@ def normalize_power(v, a):
     v = _f64(v).copy()
     lib.orc_normalize_power(_p(v), v.size, a)
     return v
+
+
+_rot_keepalive = None
+
+
+def set_rotation(R):
+    """install (or clear with None) the RandomRotation matrix the encode / search functions apply (PQ.java:237-241)"""
+    global _rot_keepalive
+    if R is None:
+        _rot_keepalive = None
+        lib.orc_set_rotation(None, 0)
+    else:
+        _rot_keepalive = _f64(R)
+        lib.orc_set_rotation(_p(_rot_keepalive), _rot_keepalive.shape[0])
+
+
+def apply_rotation(R, v):
+    R, v = _f64(R), _f64(v)
+    out = np.empty_like(v)
+    lib.orc_apply_rotation(_p(R), R.shape[0], _p(v), _p(out))
+    return out
+
+
+def pca_project(Vt, means, X, l2=False):
+    """PCA.sampleToEigenSpace for every row of X"""
+    Vt, means, X = _f64(Vt), _f64(means), _f64(X)
+    nc, ss = Vt.shape
+    out = np.empty((X.shape[0], nc), np.float64)
+    for i in range(X.shape[0]):
+        lib.orc_pca_project(_p(Vt), _p(means), nc, ss, _p(X[i]), 1 if l2 else 0, _p(out[i]))
+    return out
+
+
+def vlad_multi(codebooks, desc, offsets, normalize=True, threads=1):
+    """VladAggregatorMultipleVocabularies.aggregate VAMV.java:84-101 over a batch of images"""
+    subs = []
+    for cb in codebooks:
+        sub, _ = vlad(cb, desc, offsets, threads=threads)
+        if normalize:
+            sub = np.stack([normalize_l2(normalize_power(r, 0.5)) for r in sub])
+        subs.append(sub)
+    multi = np.concatenate(subs, axis=1)
+    if normalize and len(codebooks) > 1:
+        multi = np.stack([normalize_l2(r) for r in multi])
+    return multi

@@ -435,3 +435,209 @@ def test_config4_geometry_large_batch():
     off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
     ref = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=O.num_threads())
     assert_same(ix.searchBatch(k, Q), ref, "m=16 large batch")
+
+
+# ---------------------------------------------------------------- fp32 range of the filters
+@pytest.mark.parametrize("db_scale,q_scale", [(1e-25, 1e-25), (1e25, 1e25), (1.0, 1e20), (1.0, 1e-20), (1e-10, 1e-10)])
+def test_fast_path_is_exact_outside_the_fp32_range(db_scale, q_scale):
+    """Data far outside fp32's comfortable range: the fp32 filters (coarse and ADC) must not be trusted there.  An index
+    outside the magnitude window takes the binary64 kernels, a query outside it is evaluated by the table-free exact
+    kernel; inside the window the filter carries an absolute underflow slack.  Same bits as the oracle in every case."""
+    d, m, ks, nlist, w, n, nq, k = 64, 8, 256, 32, 8, 12000, 48, 50
+    ce = synth.mixture_centers(d, 64)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce) * db_scale, synth.mixture(nq, d, synth.SEED_Q, ce) * q_scale
+    Q[::7] = synth.mixture(nq, d, 5, ce)[::7] * db_scale  # some queries at the database's own scale
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=4000, iters=3, centers=ce)
+    Cq, P = Cq * db_scale, P * db_scale
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    ol, oc = O.ivfpq_encode(Cq, P, X, threads=8)
+    assert (lists == ol).all() and (codes == oc).all()
+    assert (ix.computeNearestCoarseIndices(Q) == O.coarse_topw(Cq, Q, w)).all()
+    off, cc, ii = synth.csr_from_assignments(ol, oc, nlist)
+    assert_same(ix.searchBatch(k, Q), O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=8), f"scale {db_scale:g}/{q_scale:g}")
+    pq = M.PQ(d, n, m, ks)
+    pq.loadProductQuantizer(P)
+    _, pc = pq.indexVectors(None, X, return_codes=True)
+    assert_same(pq.searchBatch(k, Q), O.pq_search(P, pc, Q, k, threads=8), f"flat scale {db_scale:g}/{q_scale:g}")
+
+
+def test_results_do_not_depend_on_the_tie_rule_when_no_boundary_tie_exists():
+    """The oracle's queue tie rule is restated from memory (LingPipe is un-vendored).  Property: a query
+    whose k-th and (k+1)-th exact distances differ has ONE possible id set and distance list whatever the tie rule is --
+    plain sort of the exact distances.  So for those queries the GPU result must equal a rule-free reference; the count
+    of the others is what bench.py reports as ties_at_k_boundary."""
+    d, m, ks, nlist, w, n, nq, k = 64, 8, 256, 32, 8, 15000, 200, 40
+    ce = synth.mixture_centers(d, 64)
+    X = synth.mixture(n, d, synth.SEED_DB, ce) + np.random.default_rng(0).normal(0, 0.3, (n, d))  # de-duplicated codes
+    Q = synth.mixture(nq, d, synth.SEED_Q, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=5000, iters=3, centers=ce)
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    iids, dist, cnt, _ = ix.searchBatch(k, Q)
+    i1, d1, c1, _ = ix.searchBatch(k + 1, Q)
+    probes = ix.computeNearestCoarseIndices(Q)
+    untied = 0
+    for r in range(nq):
+        # rule-free reference: exact ADC distance of every candidate (the library's own binary64 tables), plain sort
+        cand, dd = [], []
+        for l in probes[r]:
+            idx = np.nonzero(lists == l)[0]
+            lut = ix.computeLookupADC((Cq[l] - Q[r]).reshape(1, -1))[0]  # residual = centroid - query (IVFPQ.java:645)
+            acc = np.zeros(len(idx))
+            for j in range(m):  # l2distance += LUT[j][code_j], j ascending from 0.0 (IVFPQ.java:435-438)
+                acc = acc + lut[j, codes[idx, j]]
+            cand.append(idx)
+            dd.append(acc)
+        cand, dd = np.concatenate(cand), np.concatenate(dd)
+        order = np.argsort(dd, kind="stable")
+        if len(cand) > k and dd[order[k - 1]] == dd[order[k]]:
+            continue  # a boundary tie: membership depends on the queue rule (covered by the oracle comparison)
+        untied += 1
+        top = order[:k]
+        assert set(cand[top]) == set(iids[r, :cnt[r]]), r
+        assert (np.sort(dd[top]) == dist[r, :cnt[r]]).all(), r
+        assert c1[r] <= k or d1[r, k - 1] != d1[r, k]  # the k+1 search sees the same boundary
+    assert untied >= nq * 0.9
+
+
+def test_concurrent_searches_and_vlad_from_four_threads():
+    """computeNearestNeighbors is unsynchronised in the reference (ASS.java:281) and VladAggregator.aggregate is
+    called from pool threads on one shared aggregator (ImageVectorization.java:60,198): both must be re-entrant here."""
+    import threading
+    d, m, ks, nlist, w, n, k = 64, 8, 256, 32, 8, 20000, 30
+    ce = synth.mixture_centers(d, 64)
+    X = synth.mixture(n, d, synth.SEED_DB, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=4000, iters=3, centers=ce)
+    ix = make_ivfpq(d, m, ks, nlist, w, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    desc, offs = synth.descriptors(40, 32)
+    cb = synth.kmeans(desc[:4000], 16, 3, seed=1)
+    agg = M.VladAggregator(cb)
+    vref, _ = O.vlad(cb, desc, offs)
+    sizes = [1, 33, 700, 5000]  # single query, small batch, one chunk, pipelined multi-chunk path
+    Qs = [synth.mixture(s, d, 10 + t, ce) for t, s in enumerate(sizes)]
+    refs = [O.ivfpq_search(Cq, P, off, cc, ii, q, k, w, threads=8) for q in Qs]
+    ix.searchBatch(k, Qs[1])  # seal + tables before the threads start
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(6):
+                assert_same(ix.searchBatch(k, Qs[t]), refs[t], f"thread {t} rep {rep}")
+                out, _ = agg.aggregateBatch((desc, offs))
+                assert (out == vref.reshape(out.shape)).all(), f"vlad thread {t} rep {rep}"
+        except BaseException as e:  # noqa: BLE001
+            errors.append(f"thread {t}: {e!r}")
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+
+
+# ---------------------------------------------------------------- rows f2, f3, f4 on the device
+def test_vlad_multi_vocabulary_and_normalizations():
+    """VladAggregatorMultipleVocabularies (VAMV.java:84-101) and Normalization.java on the device vs the oracle: the L2 step is
+    bit-identical (ordered sum of squares); power(0.5) is the correctly rounded root where Math.pow / libm pow may differ in
+    the last bit, hence the 1e-12 bound on the normalised values."""
+    rng = np.random.default_rng(2)
+    D = 16
+    codebooks = [rng.normal(size=(K, D)) for K in (8, 5, 12)]
+    images = [rng.normal(size=(n, D)) for n in (30, 1, 0, 77, 400)]
+    offsets = np.zeros(len(images) + 1, np.int64)
+    offsets[1:] = np.cumsum([len(im) for im in images])
+    desc = np.concatenate(images)
+    mv = M.VladAggregatorMultipleVocabularies(codebooks)
+    assert mv.getVectorLength() == (8 + 5 + 12) * D and mv.isNormalizationsOn()
+    out = mv.aggregateBatch(images)
+    ref = O.vlad_multi(codebooks, desc, offsets, normalize=True)
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-300)
+    assert np.allclose(out[2], 1.0 / np.sqrt(mv.getVectorLength()))  # empty image: zero sub-VLADs are filled with ones (sic)
+    assert np.allclose(mv.aggregate(images[0]), ref[0], rtol=1e-12, atol=0)
+    mv.setNormalizationsOn(False)
+    assert (mv.aggregateBatch(images) == O.vlad_multi(codebooks, desc, offsets, normalize=False)).all()  # plain concatenation
+    # Normalization.java stand-alone, incl. a row longer than one staging chunk and the zero row
+    for n in (1, 7, 4096, 4097, 32768):
+        v = rng.normal(size=n) * rng.uniform(0.1, 100)
+        assert (M.normalizeL2(v) == O.normalize_l2(v)).all(), n
+    B = rng.normal(size=(9, 513))
+    B[4] = 0
+    nb = M.normalizeL2(B)
+    for i in range(9):
+        assert (nb[i] == O.normalize_l2(B[i])).all()
+    assert (B[4] == 0).all()  # the mirror returns copies
+    v = np.concatenate([rng.normal(size=5000) * 10, [0.0, -0.0, 1e-300, -1e300]])
+    for a in (0.5, 0.3, 1.0):
+        p, q = M.normalizePower(v, a), O.normalize_power(v, a)
+        assert np.allclose(p, q, rtol=1e-12, atol=0) and (np.sign(p) == np.sign(v)).all()
+    s = M.normalizeSSR(v[:5000])
+    assert np.allclose(s, O.normalize_l2(O.normalize_power(v[:5000], 0.5)), rtol=1e-12, atol=0)
+
+
+def test_pca_projection_vs_oracle():
+    """PCA.sampleToEigenSpace (PCA.java:188-208): the device product adds a row's products for j ascending like the oracle, so
+    the projection is bit-identical to it; 1e-4 relative is the bound claimed against the Java path (EJML un-vendored)."""
+    from multimedia_indexing_b200.dimreduction import PCA
+    rng = np.random.default_rng(0)
+    for d, nc, n in ((24, 6, 50), (1000, 100, 333), (64, 64, 1)):
+        A = rng.normal(size=(max(400, 2 * d), d)) * np.linspace(3, 0.2, d)
+        mean = A.mean(0)
+        _, sv, Vt = np.linalg.svd(A - mean, full_matrices=False)
+        eig = sv ** 2 / (len(A) - 1)
+        X = rng.normal(size=(n, d)) * np.linspace(3, 0.2, d)
+        plain = PCA(nc, len(A), d)
+        plain.loadPCAFromFile((mean, eig, Vt))
+        Y = plain.sampleToEigenSpaceBatch(X)
+        ref = O.pca_project(plain.V_t, mean, X)
+        assert np.allclose(Y, ref, rtol=REL_TOL, atol=1e-12) and (Y == ref).all()
+        assert (plain.sampleToEigenSpace(X[0]) == Y[0]).all()
+        white = PCA(nc, len(A), d, doWhitening=True)
+        white.loadPCAFromFile((mean, eig, Vt))
+        Z = white.sampleToEigenSpaceBatch(X)
+        zr = O.pca_project(white.V_t, mean, X, l2=True)
+        assert (Z == zr).all() and np.allclose(np.linalg.norm(Z, axis=1), 1.0)
+
+
+@pytest.mark.parametrize("kind", ["ivfpq", "pq"])
+def test_random_rotation_with_a_supplied_matrix(kind):
+    """TransformationType.RandomRotation (PQ.java:237-241,294-298; IVFPQ.java:319-323,420-424): the vector / the residual is
+    multiplied by the d x d matrix (RandomRotation.java:44-49) before product quantization, at index and at search time.
+    The matrix is supplied (EJML's generator is un-vendored); codes, ids and distances equal the oracle's, bit for bit."""
+    d, m, ks, nlist, w, n, nq, k = 32, 8, 256, 16, 5, 6000, 40, 20
+    rng = np.random.default_rng(5)
+    R, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    ce = synth.mixture_centers(d, 64)
+    X, Q = synth.mixture(n, d, synth.SEED_DB, ce), synth.mixture(nq, d, synth.SEED_Q, ce)
+    v = rng.normal(size=d)
+    assert np.allclose(O.apply_rotation(R, v), v @ R, rtol=1e-12)
+    try:
+        O.set_rotation(R)
+        if kind == "ivfpq":
+            Cq = synth.kmeans(X[:3000], nlist, 3, seed=1)
+            res = np.stack([O.apply_rotation(R, Cq[l] - x) for l, x in zip(synth._assign(X[:3000], Cq), X[:3000])])
+            P = synth.train_pq_on(res, m, ks, iters=3)
+            with pytest.raises(M.MmidxError):
+                M.IVFPQ(d, n, m, ks, M.TransformationType.RandomRotation, nlist)  # no matrix: not reproducible
+            ix = M.IVFPQ(d, n, m, ks, M.TransformationType.RandomRotation, nlist, rotation=R)
+            ix.loadCoarseQuantizer(Cq)
+            ix.loadProductQuantizer(P)
+            ix.setW(w)
+            lists, codes = ix.indexVectors(None, X, return_codes=True)
+            ol, oc = O.ivfpq_encode(Cq, P, X, threads=1)
+            assert (lists == ol).all() and (codes == oc).all()
+            off, cc, ii = synth.csr_from_assignments(ol, oc, nlist)
+            assert_same(ix.searchBatch(k, Q), O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w, threads=1), "rotated ivfpq")
+        else:
+            P = synth.train_pq_on(np.stack([O.apply_rotation(R, x) for x in X[:3000]]), m, ks, iters=3)
+            pq = M.PQ(d, n, m, ks, M.TransformationType.RandomRotation, rotation=R)
+            pq.loadProductQuantizer(P)
+            _, codes = pq.indexVectors(None, X, return_codes=True)
+            oc = O.pq_encode(P, X, threads=1)
+            assert (codes == oc).all()
+            assert_same(pq.searchBatch(k, Q), O.pq_search(P, oc, Q, k, threads=1), "rotated pq")
+    finally:
+        O.set_rotation(None)
