@@ -871,6 +871,14 @@ def run_gpu_cfg4(args, ctx, M, synth, wl):
     torch.cuda.synchronize()
     lists, codes = d_lists.cpu().numpy(), d_codes.cpu().numpy()
     del d_lists, d_codes
+    # every rank generated and encoded the database itself: the copies must be identical
+    chk = torch.tensor([float(np.bitwise_xor.reduce(codes.view(np.uint64).ravel()) % (1 << 52)), float(lists.astype(np.int64).sum())],
+                       dtype=torch.float64, device=ctx.dev)
+    lo, hi = chk.clone(), chk.clone()
+    if ctx.dist is not None:
+        ctx.dist.all_reduce(lo, op=ctx.dist.ReduceOp.MIN)
+        ctx.dist.all_reduce(hi, op=ctx.dist.ReduceOp.MAX)
+    same_db = bool((lo == hi).all().item())
     log(f"[bench] rank {rank}: indexed {N_DB} vectors (device-generated) in {time.time() - t0:.1f}s")
     per = (NQ + world - 1) // world
     mi1.connect(max_gq=max(per, NQ if world == 1 else per), k_max=K)
@@ -933,7 +941,7 @@ def run_gpu_cfg4(args, ctx, M, synth, wl):
         return
     head_name = "sharded" if world > 1 else "replicas"
     head, h_iids, h_dist = results[head_name]
-    parity = {}
+    parity = {"database_identical_on_all_ranks": same_db}
     if not args.no_cpu_baseline:
         O = oracle()
         off, cc, ii = synth.csr_from_assignments(lists, codes, wl["NLIST"])
@@ -945,8 +953,16 @@ def run_gpu_cfg4(args, ctx, M, synth, wl):
         ol, ocodes = O.ivfpq_encode(Cq, P, keep_x[0][:ne], threads=O.num_threads())
         parity[f"codes_first_{ne}_equal_to_oracle"] = bool((ol == lists[:ne]).all() and (np.asarray(ocodes) == codes[:ne]).all())
     if world > 1:
-        parity["sharded_equals_replicas_all_rows"] = bool((results["sharded"][1][:NQ] == results["replicas"][1][:NQ]).all() and
-                                                          (results["sharded"][2][:NQ] == results["replicas"][2][:NQ]).all())
+        si, sd = results["sharded"][1][:NQ], results["sharded"][2][:NQ]
+        ri, rd = results["replicas"][1][:NQ], results["replicas"][2][:NQ]
+        parity["sharded_equals_replicas_all_rows"] = bool((si == ri).all() and (sd == rd).all())
+        bad = np.nonzero((si != ri).any(axis=1) | (sd != rd).any(axis=1))[0]
+        if len(bad):  # diagnostics for a failing run
+            q = int(bad[0])
+            parity["mismatching_queries"] = int(len(bad))
+            parity["first_mismatch"] = {"query": q, "same_id_set": bool(set(si[q]) == set(ri[q])), "same_dist_multiset": bool((np.sort(sd[q]) == np.sort(rd[q])).all()),
+                                        "first_col": int(np.nonzero((si[q] != ri[q]) | (sd[q] != rd[q]))[0][0]),
+                                        "sharded": [int(x) for x in si[q][:6]], "replicas": [int(x) for x in ri[q][:6]]}
     peak, peak_src = peaks()
     scan_ms = head["stage_ms_per_step"]["scan"]
     per_gpu_bytes = scan_bytes_total / world if world > 1 else scan_bytes_total

@@ -99,7 +99,9 @@ int mmidx_add_codes(mmidx_t *ix, int64_t n, const int32_t *list_ids, const void 
 /* encode only, nothing stored (the arithmetic of indexVectorInternal without the append) */
 int mmidx_encode(mmidx_t *ix, int64_t n, const double *X, int32_t *out_list, void *out_codes);
 /* mmidx_add with the vectors already in HBM: dX[n][d], d_out_list / d_out_codes are DEVICE pointers (may be NULL).
- * Lets a caller index a database that is produced on the device (bench.py configs[3]: 10M vectors per shard). */
+ * Lets a caller index a database that is produced on the device (bench.py configs[3]: 10M vectors per shard).
+ * Runs on the index's own stream and returns when the vectors are stored: dX must be COMPLETE when the call is made
+ * (synchronise the stream that produces it first). */
 int mmidx_add_dev(mmidx_t *ix, int64_t n, const double *dX, int32_t *d_out_list, void *d_out_codes);
 
 /* ---- search: computeNearestNeighborsInternal(k, double[]) (IVFPQ.java:408-450 computeKnnIVFADC,

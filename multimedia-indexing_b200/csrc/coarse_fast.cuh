@@ -13,6 +13,8 @@
 // queue's order and tie rule -- the survivors contain every centroid at distance <= T, so the rule is replayed locally.
 // A query whose band holds more survivors than the collector can keep is ranked by the exact sweep in the same kernel.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tie_resolve.cuh"
@@ -98,12 +100,182 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_f32(const double *__restric
     }
 }
 
+// ---- the same filter matrix on the tensor cores (north_star: "tensor cores only for the batched coarse-quantizer GEMM") ----
+// bf16 x 3 split: q = qh + ql + eq, C = ch + cl + ec with bf16 qh, ql, ch, cl (|ql| <= 2^-9 |q|, |eq| <= (2^-18 + 2^-24) |q|),
+//   q.C ~= sum_j qh ch + (qh cl + ql ch)                                (the ql cl term is dropped)
+// evaluated with mma.sync.m16n8k16 (SASS HMMA.16816.F32.BF16): bf16 x bf16 products are exact in fp32; the main chain and the
+// 2^-9-times-smaller correction chain have their own fp32 accumulators.  Because the filter is only ever used to REJECT
+// (k_coarse_verify ranks the survivors on exact binary64 distances) it needs a valid error radius, not IEEE semantics:
+//   representation   |q.C - split| <= 3.1 * 2^-18 ||q|| ||C||
+//   accumulation     one HMMA adds 16 exact products to the accumulator; modelled as |err| <= 2^-18 (sum |products| + |acc|)
+//                    (published measurements of NVIDIA tensor cores: truncation to the largest addend's ulp, <= 17 * 2^-23;
+//                    2^-18 doubles that), d/16 instructions per chain: <= 2^-18 (1 + d/16) ||q|| ||C||
+//   fp32 epilogue    c2 - 2 (main + corr): a few u
+// => coefficient TC_COEF(d) on ||q|| Cmax below (k_coarse_verify's radius takes it instead of the FFMA one).  The
+// accumulation model is an assumption about the hardware, so mmidx_set_coarse_quantizer MEASURES the kernel against binary64
+// on the loaded centroids before enabling it (self_check_coarse_mma; margin 4x) and falls back to k_coarse_f32 otherwise.
+__host__ __device__ inline double coarse_coef_ffma(int d) { return 1.02 * 5.9604644775390625e-08 * (2.0 * d + 8.0); }
+__host__ __device__ inline double coarse_coef_mma(int d) {
+    return 1.05 * 2.0 * 3.814697265625e-06 * (3.1 + 1.0 + d / 16.0) + 8.0 * 5.9604644775390625e-08;
+}
+
+// Ch / Cl: bf16 split of the coarse centroids, [nlist][dpad] (dpad = d rounded up to 16, zero filled)
+__global__ void k_coarse_split_tables(const double *__restrict__ C, int nlist, int d, int dpad, unsigned short *__restrict__ Ch,
+                                      unsigned short *__restrict__ Cl) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)nlist * dpad) return;
+    const int c = (int)(e / dpad), j = (int)(e - (int64_t)c * dpad);
+    float f = 0.f;
+    if (j < d) f = __double2float_rn(C[(int64_t)c * d + j]);
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    const __nv_bfloat16 l = __float2bfloat16_rn(f - __bfloat162float(h));
+    Ch[e] = __bfloat16_as_ushort(h);
+    Cl[e] = __bfloat16_as_ushort(l);
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// CTA tile 128 queries x 64 centroids, 8 warps as 4 x 2, warp tile 32 x 32 (2 x 4 HMMA tiles), K chunk 64.
+// Shared rows are padded to 72 bf16 (36 words): the 8 rows a fragment load touches fall into distinct banks.
+constexpr int TM_BM = 128, TM_BN = 64, TM_BK = 64, TM_LD = TM_BK + 8;
+constexpr size_t TM_SMEM = (size_t)2 * (TM_BM + TM_BN) * TM_LD * sizeof(unsigned short);
+
+__global__ void __launch_bounds__(MMIDX_NT) k_coarse_mma(const double *__restrict__ Q, const unsigned short *__restrict__ Ch,
+                                                         const unsigned short *__restrict__ Cl, const float *__restrict__ c2,
+                                                         int64_t nq, int nlist, int d, int dpad, float *__restrict__ A32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned short *Ah = reinterpret_cast<unsigned short *>(smem_raw);  // [TM_BM][TM_LD]
+    unsigned short *Al = Ah + TM_BM * TM_LD;
+    unsigned short *Bh = Al + TM_BM * TM_LD;                            // [TM_BN][TM_LD]
+    unsigned short *Bl = Bh + TM_BN * TM_LD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;  // warp tile origin: rows wm*32, columns wn*32
+    const int g = lane >> 2, tig = lane & 3;
+    const int64_t q0 = (int64_t)blockIdx.y * TM_BM;
+    const int n0 = blockIdx.x * TM_BN;
+    float main_[2][4][4], corr[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) main_[i][j][r] = corr[i][j][r] = 0.f;
+    for (int k0 = 0; k0 < dpad; k0 += TM_BK) {
+        __syncthreads();
+        // queries: binary64 -> fp32 -> bf16 hi / lo
+        for (int e = tid; e < TM_BM * TM_BK; e += MMIDX_NT) {
+            const int r = e / TM_BK, kk = e - r * TM_BK;
+            const int64_t q = q0 + r;
+            const int col = k0 + kk;
+            float f = 0.f;
+            if (q < nq && col < d) f = __double2float_rn(Q[q * (int64_t)d + col]);
+            const __nv_bfloat16 h = __float2bfloat16_rn(f);
+            Ah[r * TM_LD + kk] = __bfloat16_as_ushort(h);
+            Al[r * TM_LD + kk] = __bfloat16_as_ushort(__float2bfloat16_rn(f - __bfloat162float(h)));
+        }
+        // centroids: 128-bit copies of the split tables
+        for (int e = tid; e < TM_BN * (TM_BK / 8); e += MMIDX_NT) {
+            const int r = e / (TM_BK / 8), k8 = (e - r * (TM_BK / 8)) * 8;
+            const int n = n0 + r;
+            uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+            if (n < nlist && k0 + k8 < dpad) {
+                vh = *reinterpret_cast<const uint4 *>(Ch + (int64_t)n * dpad + k0 + k8);
+                vl = *reinterpret_cast<const uint4 *>(Cl + (int64_t)n * dpad + k0 + k8);
+            }
+            *reinterpret_cast<uint4 *>(Bh + r * TM_LD + k8) = vh;
+            *reinterpret_cast<uint4 *>(Bl + r * TM_LD + k8) = vl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < TM_BK; ks += 16) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = wm * 32 + i * 16 + g;
+                const int c = ks + 2 * tig;
+                ah[i][0] = *reinterpret_cast<const uint32_t *>(Ah + r * TM_LD + c);
+                ah[i][1] = *reinterpret_cast<const uint32_t *>(Ah + (r + 8) * TM_LD + c);
+                ah[i][2] = *reinterpret_cast<const uint32_t *>(Ah + r * TM_LD + c + 8);
+                ah[i][3] = *reinterpret_cast<const uint32_t *>(Ah + (r + 8) * TM_LD + c + 8);
+                al[i][0] = *reinterpret_cast<const uint32_t *>(Al + r * TM_LD + c);
+                al[i][1] = *reinterpret_cast<const uint32_t *>(Al + (r + 8) * TM_LD + c);
+                al[i][2] = *reinterpret_cast<const uint32_t *>(Al + r * TM_LD + c + 8);
+                al[i][3] = *reinterpret_cast<const uint32_t *>(Al + (r + 8) * TM_LD + c + 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = wn * 32 + j * 8 + g;
+                const int c = ks + 2 * tig;
+                bh[j][0] = *reinterpret_cast<const uint32_t *>(Bh + n * TM_LD + c);
+                bh[j][1] = *reinterpret_cast<const uint32_t *>(Bh + n * TM_LD + c + 8);
+                bl[j][0] = *reinterpret_cast<const uint32_t *>(Bl + n * TM_LD + c);
+                bl[j][1] = *reinterpret_cast<const uint32_t *>(Bl + n * TM_LD + c + 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    mma_bf16_16816(main_[i][j], ah[i], bh[j]);
+                    mma_bf16_16816(corr[i][j], ah[i], bl[j]);
+                    mma_bf16_16816(corr[i][j], al[i], bh[j]);
+                }
+        }
+    }
+    // a = c2[c] - 2 (main + corr)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int64_t q = q0 + wm * 32 + i * 16 + g + half * 8;
+            if (q >= nq) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * tig;
+                const float d0 = main_[i][j][half * 2] + corr[i][j][half * 2];
+                const float d1 = main_[i][j][half * 2 + 1] + corr[i][j][half * 2 + 1];
+                if (n < nlist) A32[q * (int64_t)nlist + n] = fmaf(-2.f, d0, c2[n]);
+                if (n + 1 < nlist) A32[q * (int64_t)nlist + n + 1] = fmaf(-2.f, d1, c2[n + 1]);
+            }
+        }
+}
+
+// max over a sample of |a32 - (||C||^2 - 2 q.C)| / (||q|| Cmax) in binary64: what mmidx_set_coarse_quantizer compares with
+// the coefficient above.  Queries = the first nsamp centroids (perturbed by the caller); one thread per (q, c) pair.
+__global__ void k_coarse_filter_error(const double *__restrict__ Q, const double *__restrict__ C, const float *__restrict__ A32,
+                                      int nsamp, int nlist, int d, double cmax, double *__restrict__ out_max) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double ratio = 0.0;
+    if (e < (int64_t)nsamp * nlist) {
+        const int q = (int)(e / nlist), c = (int)(e - (int64_t)q * nlist);
+        double dot = 0.0, c2 = 0.0, q2 = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double qv = Q[(int64_t)q * d + j], cv = C[(int64_t)c * d + j];
+            dot = fma(qv, cv, dot);
+            c2 = fma(cv, cv, c2);
+            q2 = fma(qv, qv, q2);
+        }
+        const double t = c2 - 2.0 * dot;
+        const double den = sqrt(q2) * cmax;
+        // the c2 rounding (u Cmax^2) is accounted for separately in the radius: take it out of the measurement
+        const double err = fmax(0.0, fabs((double)A32[e] - t) - 1.2e-7 * cmax * cmax);
+        ratio = den > 0.0 ? err / den : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+    if ((threadIdx.x & 31) == 0 && ratio > 0.0)
+        atomicMax(reinterpret_cast<unsigned long long *>(out_max), (unsigned long long)__double_as_longlong(ratio));
+}
+
 // grid nq.  Shared memory: TopK<CAP> | qv [d] | keys [nlist] fp32 | surv [CAP] | xs [vb][d + 1]
 
 template <int CAP>
 __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__restrict__ Q, const double *__restrict__ C,
                                                             const float *__restrict__ A32, const float *__restrict__ cmax,
-                                                            int nlist, int d, int w, int vb, TopkOut o) {
+                                                            int nlist, int d, int w, int vb, double coef, TopkOut o) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TopK<CAP> &tk = *reinterpret_cast<TopK<CAP> *>(smem_raw);
     const size_t tk_bytes = (sizeof(TopK<CAP>) + 127) & ~(size_t)127;
@@ -189,7 +361,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
     if (!(kth <= 3.4028234663852886e38f)) kth = 3.4028234663852886e38f;  // prefix of inf / nan patterns
     // ---- survivors: a <= kth + 2B ----
     const double qn = sqrt(s_q2) * (1.0 + 1e-12), cm = (double)cmax[0];
-    const double B = 1.02 * 5.9604644775390625e-08 * (2.0 * cm * cm + (2.0 * d + 8.0) * qn * cm) +
+    // coef: coarse_coef_ffma(d) or coarse_coef_mma(d), whichever kernel produced A32
+    const double B = 1.02 * 5.9604644775390625e-08 * 2.0 * cm * cm + coef * qn * cm +
                      (d + 2.0) * 2.220446049250313e-16 * (qn + cm) * (qn + cm);
     const float lim = __double2float_ru((double)kth + 2.0 * B + 1e-30);
     for (int i0 = 0; i0 < nlist; i0 += MMIDX_NT) {

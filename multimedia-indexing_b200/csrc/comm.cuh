@@ -169,9 +169,16 @@ struct TieMultiArgs {
     int S, shard, sl;
 };
 
-__global__ void __launch_bounds__(MMIDX_NT) k_tie_collect_multi(TieMultiArgs a) {
+// Per probed list the exact binary64 ADC table is rebuilt in shared memory (same arithmetic as k_lut_build:
+// computeResidualVector IVFPQ.java:642-648 + computeLookupADC :525-538) and the list is swept in offer order with m lookups
+// per candidate -- ~50 us per flagged query instead of re-deriving every candidate from the quantizers.  use_lut == 0
+// (table larger than the shared memory the host granted): table-free evaluation.
+__global__ void __launch_bounds__(MMIDX_NT) k_tie_collect_multi(TieMultiArgs a, int use_lut) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_sums[MMIDX_NT / 32];
     const TieDirectArgs &r = a.t;
+    double *rv = reinterpret_cast<double *>(smem_raw);  // [d]   transformed residual of the current probe
+    double *lut = rv + r.d;                             // [m][ks]
     for (int owner = 0; owner < a.S; ++owner) {
         const int na = a.a_cnt[owner];
         unsigned char *b = a.base[owner];
@@ -195,9 +202,29 @@ __global__ void __launch_bounds__(MMIDX_NT) k_tie_collect_multi(TieMultiArgs a) 
                 const double *Cl = r.C + (int64_t)(r.flat ? 0 : l) * r.d;
                 const uint8_t *cp = r.codes + start * r.code_bytes;
                 const int32_t *li = r.iids + start;
-                tie_sweep(len, ((unsigned long long)p) << 32, T, r.k, found, warp_sums, o, ql,
-                          [=](int64_t i) { return exact_adc(Cl, qv, r.perm, r.P, cp + i * r.code_bytes, r.m, r.ks, r.S); },
-                          [li](int64_t i) { return li[i]; });
+                if (use_lut) {
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < r.d; i += MMIDX_NT) {
+                        const int src = r.perm ? r.perm[i] : i;
+                        rv[i] = __dsub_rn(Cl[src], qv[src]);  // residual = centroid - query, then the permutation
+                    }
+                    __syncthreads();
+                    for (int e = threadIdx.x; e < r.m * r.ks; e += MMIDX_NT) {
+                        const int j = e / r.ks, c = e - j * r.ks;
+                        const double *pc = r.P + ((int64_t)j * r.ks + c) * r.S;
+                        double acc = 0.0;
+                        for (int t = 0; t < r.S; ++t) acc = sqacc(acc, rv[j * r.S + t], pc[t]);
+                        lut[e] = acc;
+                    }
+                    __syncthreads();
+                    const int m = r.m, ks = r.ks, cb = r.code_bytes;
+                    tie_sweep(len, ((unsigned long long)p) << 32, T, r.k, found, warp_sums, o, ql,
+                              [=](int64_t i) { return adc_dist(lut, cp + i * cb, m, ks); }, [li](int64_t i) { return li[i]; });
+                } else {
+                    tie_sweep(len, ((unsigned long long)p) << 32, T, r.k, found, warp_sums, o, ql,
+                              [=](int64_t i) { return exact_adc(Cl, qv, r.perm, r.P, cp + i * r.code_bytes, r.m, r.ks, r.S); },
+                              [li](int64_t i) { return li[i]; });
+                }
             }
             if (threadIdx.x == 0) o.cnt[ql] = min(found, r.k);
             __syncthreads();

@@ -607,6 +607,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
     float *qn = reinterpret_cast<float *>(qv + d);      // [m]  upper bound of ||q_j||
     float *bterm = qn + m;                              // [m]
     int *slot_of = reinterpret_cast<int *>(bterm + m);  // [w]  descriptor slot of probe rank p, -1: not on this shard
+    int *lst = slot_of + w;                             // [w]  list id of probe rank p (staged: the sums below then issue
+                                                        //      independent centroid loads instead of a probe -> row chain)
     const int tid = threadIdx.x;
     const int64_t q = blockIdx.x;
     const int dstride = fast_desc_stride(m);
@@ -635,6 +637,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
             if (p < w) {
                 l = pr[p];
                 len = list_len[l];
+                lst[p] = flat ? 0 : l;
             }
             cand += len;
             const bool own = len > 0;
@@ -667,11 +670,12 @@ __global__ void __launch_bounds__(MMIDX_NT) k_fast_prep(const double *__restrict
         constexpr int SS = ST > 0 ? ST : 1;
         constexpr int per_warp = 32 / SS;
         const int sub = lane / SS, t = lane - sub * SS;
+#pragma unroll 4
         for (int e0 = warp * per_warp; e0 < w * m; e0 += (MMIDX_NT / 32) * per_warp) {
             const int e = e0 + sub;
             const bool valid = e < w * m;
             const int p = valid ? e / m : 0, j = valid ? e - p * m : 0;
-            const int l = flat ? 0 : pr[p];
+            const int l = lst[p];
             const int slot = slot_of[p];
             const bool use = valid && slot >= 0;
             int src = j * S + t;

@@ -236,6 +236,10 @@ struct mmidx_index {
     DevBuf dPneg;             // flat PQ on the fused path: -P (the index is an IVFPQ with one zero centroid, fast_scan.cuh)
     int flat_nlist = 0;       // ... and its pseudo lists of equal length
     DevBuf dC32, dc2, dcmax;  // coarse_fast.cuh: fp32 copy of the coarse quantizer, ||C||^2, max ||C||
+    DevBuf dCh, dCl;          // ... and its bf16 hi / lo split for the tensor-core filter (k_coarse_mma)
+    int dpad = 0;             // d rounded up to 16
+    bool coarse_mma_ok = false;   // the tensor-core filter passed its measurement against binary64 on this quantizer
+    double coarse_mma_measured = 0.0;  // measured error coefficient (of ||q|| Cmax), for mmidx_debug / logs
     std::vector<int32_t> shard_map;  // optional list -> owning shard (default l % shard_count)
     bool fast_ready = false;
     bool fast_len_ok = true;   // every list shorter than 2^22 entries (packed payload of the fp32 collector)
@@ -469,10 +473,45 @@ extern "C" int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C) {
                                                              ix->dc2.as<float>(), ix->dcmax.as<float>());
     RET(post_launch("k_coarse_tables", nullptr));
     CK(cudaStreamSynchronize(ix->stream));
-    {
-        float cm = 0.f;
-        CK(cudaMemcpy(&cm, ix->dcmax.p, sizeof(float), cudaMemcpyDeviceToHost));
-        ix->coarse_range_ok = fast_mag_ok((double)cm);  // false for inf / NaN too
+    float cm = 0.f;
+    CK(cudaMemcpy(&cm, ix->dcmax.p, sizeof(float), cudaMemcpyDeviceToHost));
+    ix->coarse_range_ok = fast_mag_ok((double)cm);  // false for inf / NaN too
+    // tensor-core filter: bf16 split tables, then MEASURE the kernel against binary64 on this quantizer (queries = the
+    // first centroids) before trusting the error model of coarse_fast.cuh
+    ix->coarse_mma_ok = false;
+    ix->dpad = (ix->p.d + 15) & ~15;
+    const char *cmode = getenv("MMIDX_COARSE");
+    if (ix->coarse_range_ok && cm > 0.f && !(cmode && strcmp(cmode, "ffma") == 0)) {
+        const int d = ix->p.d, nlist = ix->p.nlist, dpad = ix->dpad;
+        const size_t ce = (size_t)nlist * dpad;
+        RET(ix->dCh.reserve(ce * sizeof(unsigned short), 0, ix->stream));
+        RET(ix->dCl.reserve(ce * sizeof(unsigned short), 0, ix->stream));
+        k_coarse_split_tables<<<(unsigned)((ce + 255) / 256), 256, 0, ix->stream>>>(ix->dC.as<double>(), nlist, d, dpad,
+                                                                                   ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>());
+        RET(post_launch("k_coarse_split_tables", nullptr));
+        const int nsamp = std::min(nlist, 256);
+        Scratch sc(ix->stream);
+        float *A32;
+        double *dmax;
+        RET(sc.get(&A32, (size_t)nsamp * nlist));
+        RET(sc.get(&dmax, 1));
+        CK(cudaMemsetAsync(dmax, 0, sizeof(double), ix->stream));
+        RET(set_smem(k_coarse_mma, TM_SMEM));
+        dim3 gg((unsigned)((nlist + TM_BN - 1) / TM_BN), (unsigned)((nsamp + TM_BM - 1) / TM_BM));
+        k_coarse_mma<<<gg, MMIDX_NT, TM_SMEM, ix->stream>>>(ix->dC.as<double>(), ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>(),
+                                                            ix->dc2.as<float>(), nsamp, nlist, d, dpad, A32);
+        RET(post_launch("k_coarse_mma", nullptr));
+        k_coarse_filter_error<<<(unsigned)(((size_t)nsamp * nlist + 255) / 256), 256, 0, ix->stream>>>(
+            ix->dC.as<double>(), ix->dC.as<double>(), A32, nsamp, nlist, d, (double)cm, dmax);
+        RET(post_launch("k_coarse_filter_error", nullptr));
+        double measured = 0.0;
+        CK(cudaMemcpyAsync(&measured, dmax, sizeof(double), cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        ix->coarse_mma_measured = measured;
+        ix->coarse_mma_ok = measured == measured && measured <= coarse_coef_mma(d) / 4.0;
+        if (getenv("MMIDX_VERBOSE"))
+            fprintf(stderr, "[mmidx] tensor-core coarse filter: measured error %.3g ||q|| Cmax, modelled radius %.3g -> %s\n", measured,
+                    coarse_coef_mma(d), ix->coarse_mma_ok ? "enabled" : "disabled (FFMA filter)");
     }
     ix->has_C = true;
     ix->fast_ready = false;
@@ -985,18 +1024,29 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
         // fp32 filter (tiled FFMA GEMM) + exact binary64 verification of the few centroids inside the error band
         float *A32;
         RET(sc.get(&A32, (size_t)nq * nlist));
-        dim3 gg((unsigned)((nlist + CG_BN - 1) / CG_BN), (unsigned)((nq + CG_BM - 1) / CG_BM));
-        k_coarse_f32<<<gg, MMIDX_NT, 0, st>>>(dQ, ix->dC32.as<float>(), ix->dc2.as<float>(), nq, nlist, d, A32);
-        RET(post_launch("k_coarse_f32", launches));
+        double coef;
+        if (ix->coarse_mma_ok) {
+            RET(set_smem(k_coarse_mma, TM_SMEM));
+            dim3 gg((unsigned)((nlist + TM_BN - 1) / TM_BN), (unsigned)((nq + TM_BM - 1) / TM_BM));
+            k_coarse_mma<<<gg, MMIDX_NT, TM_SMEM, st>>>(dQ, ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>(), ix->dc2.as<float>(),
+                                                        nq, nlist, d, ix->dpad, A32);
+            RET(post_launch("k_coarse_mma", launches));
+            coef = coarse_coef_mma(d);
+        } else {
+            dim3 gg((unsigned)((nlist + CG_BN - 1) / CG_BN), (unsigned)((nq + CG_BM - 1) / CG_BM));
+            k_coarse_f32<<<gg, MMIDX_NT, 0, st>>>(dQ, ix->dC32.as<float>(), ix->dc2.as<float>(), nq, nlist, d, A32);
+            RET(post_launch("k_coarse_f32", launches));
+            coef = coarse_coef_ffma(d);
+        }
         if (ccap == 256) {
             RET(set_smem(k_coarse_verify<256>, vsm));
-            k_coarse_verify<256><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, o);
+            k_coarse_verify<256><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, coef, o);
         } else if (ccap == 1024) {
             RET(set_smem(k_coarse_verify<1024>, vsm));
-            k_coarse_verify<1024><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, o);
+            k_coarse_verify<1024><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, coef, o);
         } else {
             RET(set_smem(k_coarse_verify<2048>, vsm));
-            k_coarse_verify<2048><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, o);
+            k_coarse_verify<2048><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, coef, o);
         }
         RET(post_launch("k_coarse_verify", launches));
         // only rows ranked by the kernel's exact sweep (band wider than the collector) can be flagged here
@@ -1552,7 +1602,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
             RET(sc.get(&qorder, (size_t)nq));
         }
         StageMark sm(ix, st, 1);
-        const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)w * 4 + 16;
+        const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)w * 8 + 16;
         if (M == 8 && a.S == 16)
             k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt, work);
         else if (M == 16 && a.S == 8)
@@ -2634,8 +2684,13 @@ static int multi_enqueue(mmidx_index *ix, int64_t gq, const double *dQ, int k, i
         tm.S = S;
         tm.shard = s;
         tm.sl = (int)sl;
-        k_tie_collect_multi<<<ix->sm_count, MMIDX_NT, 0, st>>>(tm);
-        RET(post_launch("k_tie_collect_multi", launches));
+        {
+            const size_t tsm = ((size_t)ix->p.m * ix->p.ks + (size_t)d) * sizeof(double);
+            const int use_lut = tsm <= 96 * 1024 ? 1 : 0;
+            if (use_lut) RET(set_smem(k_tie_collect_multi, tsm));
+            k_tie_collect_multi<<<ix->sm_count, MMIDX_NT, use_lut ? tsm : 0, st>>>(tm, use_lut);
+            RET(post_launch("k_tie_collect_multi", launches));
+        }
         RET(sync(3, false));
         RET(set_smem(k_tie_finish, (size_t)1024 * 16));
         k_tie_finish<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(nslice, 2 * ix->sm_count)), MMIDX_NT, (size_t)k * 16, st>>>(

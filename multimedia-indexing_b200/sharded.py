@@ -122,7 +122,9 @@ class MultiIVFPQ:
         self.shard_map = owner
 
     def indexDev(self, dX, d_lists=None, d_codes=None):
-        """append device-resident vectors (mmidx_add_dev); optional device outputs for the list ids / codes"""
+        """append device-resident vectors (mmidx_add_dev); optional device outputs for the list ids / codes.
+        mmidx_add_dev runs on the index's own stream: the producer of dX (torch's current stream) is synchronised first."""
+        torch.cuda.current_stream().synchronize()
         check(lib.mmidx_add_dev(self.index._h, dX.shape[0], _p(dX), _p(d_lists) if d_lists is not None else None,
                                 _p(d_codes) if d_codes is not None else None))
 

@@ -69,8 +69,10 @@ def _worker(rank, world, port, q):
         ok = True
         msgs = []
         # ---- list sharding, S = world: plain data, then heavy duplication (exact ties cut ACROSS shards) ----
-        for case in ("plain", "ties", "exact_kernels"):
+        for case in ("plain", "ties", "exact_kernels", "m16_short_lists"):
             d, m, ks, nlist, w, k, n, nq = 64, 8, 256, 64, 16, 100, 30000, 701  # odd nq: ragged last slice
+            if case == "m16_short_lists":  # configs[3] geometry: m = 16, many probes over short (and some empty) lists
+                d, m, nlist, w, n, nq = 128, 16, 512, 64, 60000, 1000
             ce = synth.mixture_centers(d, 128)
             if case == "ties":
                 base = synth.mixture(60, d, 1, ce)
