@@ -547,6 +547,10 @@ def run_gpu(args, rank, world, local_rank):
     lib = M._capi.lib
     NQ, K, W, D = wl["NQ"], wl["K"], wl["W"], wl["D"]
     ce = synth.mixture_centers(D)
+    if world > 1:  # rank 0 trains (or finds the cache the CPU arm left), everybody loads the same file
+        if rank == 0:
+            quantizers(wl, synth, ce)
+        ctx.barrier()
     Cq, P = quantizers(wl, synth, ce)
     X = synth.mixture(wl["N_DB"], D, synth.SEED_DB, ce)
     G = world
@@ -726,6 +730,12 @@ def run_gpu(args, rank, world, local_rank):
         if world == 1:
             t1_qps, t1_sample, t1_dt, _ = cpu_rate(O, wl, Cq, P, off, cc, ii, Qg, 1, 3.0)
             cpu["single_thread"] = {"value": t1_qps, "sample": f"first {t1_sample} queries, 1 thread ({t1_dt:.1f}s)"}
+            O.set_faithful_costs(True)  # BASELINE.md variant (A): the reference's allocations per candidate
+            fa_qps, fa_sample, fa_dt, (fi, fd, fc) = cpu_rate(O, wl, Cq, P, off, cc, ii, Qg, cores, 3.0)
+            O.set_faithful_costs(False)
+            cpu["allocation_faithful"] = {"value": fa_qps, "cores": cores, "same_results": bool((fi == oi[:fa_sample]).all() and (fd == od[:fa_sample]).all()),
+                                          "sample": f"first {fa_sample} queries ({fa_dt:.1f}s): per candidate a code copy, a Result and, when accepted, a queue "
+                                                    "entry are heap-allocated as in IVFPQ.java:434,443-445"}
         parity["sample_queries"] = sample
         parity["ids_equal_to_oracle"] = bool((oi == r_iids[:sample]).all())
         parity["dist_bit_equal_to_oracle"] = bool((od == r_dist[:sample]).all())

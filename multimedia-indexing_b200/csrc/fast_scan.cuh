@@ -362,8 +362,9 @@ struct TopK32 {
         }
     }
 
-    // remove every entry of probe slot `tag` (after an overflowed barrier-free scan); all threads, block-uniform
-    __device__ __noinline__ void drop_tag(unsigned int tag) {
+    // remove every entry of probe slot `tag` at list position >= pos0 (after an overflowed barrier-free scan of the list
+    // segment that starts there); all threads, block-uniform
+    __device__ __noinline__ void drop_tag(unsigned int tag, unsigned int pos0) {
         const int tid = threadIdx.x;
         const int n = min(cnt, CAP);
         float d[PER];
@@ -381,7 +382,7 @@ struct TopK32 {
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
             const int i = tid + e * MMIDX_NT;
-            if (i < n && (pp[e] >> FAST_POS_BITS) != tag) {
+            if (i < n && ((pp[e] >> FAST_POS_BITS) != tag || (pp[e] & ((1u << FAST_POS_BITS) - 1u)) < pos0)) {
                 const int slot = atomicAdd(&s_newcnt, 1);
                 key[slot] = d[e];
                 pk[slot] = pp[e];
@@ -771,6 +772,7 @@ __device__ __forceinline__ void adc_pair(const uint32_t lut, const uint4 c, floa
 
 // One list with a block barrier per ROUND candidates: the collector can never run out of slots.  Used while the
 // admission threshold is still +inf (everything is pushed) and to redo a list whose barrier-free scan overflowed.
+// lc / len: the list segment to scan; ptag already carries the segment's first list position (tag | pos0).
 template <int CAP32, int M>
 __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t lut, const uint8_t *__restrict__ lc, int len,
                                  unsigned int ptag, int k, double bq, double rel) {
@@ -795,8 +797,8 @@ __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t
             const int i0 = base + (e * MMIDX_NT + tid) * CPT;
             float d0, d1;
             adc_pair<M>(lut, cw[e], d0, d1);
-            c32.push((i0 < len) && d0 <= thr32, d0, ptag | (unsigned int)i0);
-            if (M == 8) c32.push((i0 + 1 < len) && d1 <= thr32, d1, ptag | (unsigned int)(i0 + 1));
+            c32.push((i0 < len) && d0 <= thr32, d0, ptag + (unsigned int)i0);
+            if (M == 8) c32.push((i0 + 1 < len) && d1 <= thr32, d1, ptag + (unsigned int)(i0 + 1));
         }
     }
     __syncthreads();  // every push of this list is visible
@@ -807,7 +809,15 @@ __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t
 // Per probe: one independent descriptor load, the fp32 table lut = (T1[l] + T2) + s built with 128-bit shared accesses
 // into the buffer the previous probe is not using, ONE block barrier (which also settles the collector), the TMA for
 // the next T1 row, then a barrier-free sweep over the list with the next 128-bit code load in flight.
-template <int CAP32, int M>
+// LONG: some list is longer than FAST_SEG entries (the pseudo lists of a large flat PQ index: 10^5 entries).  Such lists are
+// swept in segments of FAST_SEG entries with a settle in between, so that the admission threshold is re-read while it
+// tightens and a collector overflow re-scans one segment, not the list (without this a 1 GiB flat scan ran at 25 % of the
+// HBM peak, with it at 41 % for one query and 63 % for eight: profiles/README.md).  IVF lists are short: the LONG = false
+// instantiation is the kernel exactly as tuned for them.  (Also measured and rejected for the HBM-streaming regime: four
+// 128-bit loads in flight per thread at 3 CTAs/SM -- slower at every batch size.)
+constexpr int FAST_SEG = 8192;
+
+template <int CAP32, int M, bool LONG>
 __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
     constexpr int ECAP = FastExactCap<CAP32, M>::value;
     constexpr int ks = 256;  // the fused kernel is specialised for full byte codes (host checks ks == 256)
@@ -870,7 +880,11 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     // Settles the collector at a block barrier: if the barrier-free scan of slot `pslot` overflowed, its entries are
     // dropped and the list is scanned again with round barriers from its (still intact) table `plut`; then the buffer
     // is compacted when it is more than half full, or to get a first finite threshold.
-    auto settle = [&](int pslot, const uint32_t plut) {
+    // Settles the collector at a block barrier: if the barrier-free scan of slot `pslot` (LONG: of its segment starting at
+    // seg0) overflowed, its entries are dropped and it is scanned again with round barriers from its (still intact) table
+    // `plut`; then the buffer is compacted when it is more than half full, or to get a first finite threshold.
+    constexpr int SEG = FAST_SEG;
+    auto settle = [&](int pslot, const uint32_t plut, int seg0) {
         const int need = (c32.ovf != 0) | (*(volatile int *)&c32.cnt > KEEP) |
                          ((c32.thr32 == finf) & (*(volatile int *)&c32.cnt >= a.k));
         if (__syncthreads_or(need)) {
@@ -878,10 +892,10 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
             __syncthreads();
             if (ov) {  // block-uniform
                 if (a.stats && tid == 0) atomicAdd(&a.stats[1], 1ull);
-                c32.drop_tag((unsigned int)pslot);
+                c32.drop_tag((unsigned int)pslot, (unsigned int)seg0);
                 const ProbeHdr *h = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)pslot * DSTRIDE);
-                scan_list_rounds<CAP32, M>(c32, plut, a.ocodes + h->start * M, h->len, ((unsigned int)pslot) << FAST_POS_BITS,
-                                           a.k, a.bq[q], rel);
+                scan_list_rounds<CAP32, M>(c32, plut, a.ocodes + (h->start + seg0) * M, LONG ? min(SEG, h->len - seg0) : h->len,
+                                           (((unsigned int)pslot) << FAST_POS_BITS) + (unsigned int)seg0, a.k, a.bq[q], rel);
             }
             const int n = c32.cnt;
             const bool isinf32 = c32.thr32 == finf;
@@ -891,6 +905,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     };
 
     int it = 0;
+    int last_seg0 = 0;  // first position of the segment whose settle is still pending (the previous probe's last one)
     for (int ii = s; ii < nop; ii += a.nsplit, ++it) {
         float *lut = (it & 1) ? lut1 : lut0;
         const uint32_t lut_s = (it & 1) ? lut1_s : lut0_s;
@@ -921,41 +936,52 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
             }
         }
         // the probe's barrier: publishes the table, ends every read of `stage` and every push of the previous list
-        settle(ii - a.nsplit, (it & 1) ? lut0_s : lut1_s);
+        settle(ii - a.nsplit, (it & 1) ? lut0_s : lut1_s, last_seg0);
         if (tid == 0 && ii + a.nsplit < nop) {
             // every thread has consumed `stage`: the next probe's T1 row lands while this list is scanned
             fence_proxy_async();
             mbar_arrive_expect_tx(&bars[0], t1_bytes);
             tma_load_1d(stage, a.T1 + (int64_t)lnext * nent, t1_bytes, &bars[0]);
         }
-        const unsigned int ptag = ((unsigned int)ii) << FAST_POS_BITS;
-        const float thr32 = c32.thr32;
-        if (thr32 == finf) {  // block-uniform: nothing can be rejected yet
-            scan_list_rounds<CAP32, M>(c32, lut_s, lc, len, ptag, a.k, a.bq[q], rel);
-        } else {
-            // One 128-bit load per thread and step; the load of the next step is issued before the current one is
-            // consumed.  (Measured alternatives, profiles/README.md: L1 prefetch one or two steps ahead, two or four
-            // loads per step, 3 CTAs/SM with 80 registers -- all slower than this form.)
-            constexpr int CPT = (M == 8) ? 2 : 1;
-            constexpr int STEP = MMIDX_NT * CPT;
-            int i0 = tid * CPT;
-            uint4 cur = make_uint4(0, 0, 0, 0);
-            if (i0 < len) cur = ld_nc_u4(lc + (int64_t)i0 * M);
-            for (int wb = (tid & ~31) * CPT; wb < len; wb += STEP) {  // warp-uniform trip count
-                const int i1 = i0 + STEP;
-                uint4 nxt = make_uint4(0, 0, 0, 0);
-                if (i1 < len) nxt = ld_vol_u4(lc + (int64_t)i1 * M);
-                float d0, d1;
-                adc_pair<M>(lut_s, cur, d0, d1);
-                const bool p0 = (i0 < len) && d0 <= thr32;
-                const bool p1 = (M == 8) && (i0 + 1 < len) && d1 <= thr32;
-                if (__any_sync(0xffffffffu, p0 | p1)) c32.push2(p0, d0, p1, d1, ptag | (unsigned int)i0);
-                cur = nxt;
-                i0 = i1;
+        const unsigned int ltag = ((unsigned int)ii) << FAST_POS_BITS;
+        const uint8_t *list_codes = lc;
+        const int list_len = len;
+        for (int seg0 = 0; seg0 < (LONG ? list_len : 1); seg0 += SEG) {
+            if (LONG) {
+                if (seg0 > 0) settle(ii, lut_s, seg0 - SEG);  // block-uniform: the previous segment of this list
+                last_seg0 = seg0;
+            }
+            const uint8_t *lc = LONG ? list_codes + (int64_t)seg0 * M : list_codes;
+            const int len = LONG ? min(SEG, list_len - seg0) : list_len;
+            const unsigned int ptag = LONG ? ltag + (unsigned int)seg0 : ltag;
+            const float thr32 = c32.thr32;
+            if (thr32 == finf) {  // block-uniform: nothing can be rejected yet
+                scan_list_rounds<CAP32, M>(c32, lut_s, lc, len, ptag, a.k, a.bq[q], rel);
+            } else {
+                // One 128-bit load per thread and step; the load of the next step is issued before the current one is
+                // consumed.  (Measured alternatives, profiles/README.md: L1 prefetch one or two steps ahead, two or four
+                // loads per step, 3 CTAs/SM with 80 registers -- all slower than this form.)
+                constexpr int CPT = (M == 8) ? 2 : 1;
+                constexpr int STEP = MMIDX_NT * CPT;
+                int i0 = tid * CPT;
+                uint4 cur = make_uint4(0, 0, 0, 0);
+                if (i0 < len) cur = ld_nc_u4(lc + (int64_t)i0 * M);
+                for (int wb = (tid & ~31) * CPT; wb < len; wb += STEP) {  // warp-uniform trip count
+                    const int i1 = i0 + STEP;
+                    uint4 nxt = make_uint4(0, 0, 0, 0);
+                    if (i1 < len) nxt = ld_vol_u4(lc + (int64_t)i1 * M);
+                    float d0, d1;
+                    adc_pair<M>(lut_s, cur, d0, d1);
+                    const bool p0 = (i0 < len) && d0 <= thr32;
+                    const bool p1 = (M == 8) && (i0 + 1 < len) && d1 <= thr32;
+                    if (__any_sync(0xffffffffu, p0 | p1)) c32.push2(p0, d0, p1, d1, ptag | (unsigned int)i0);
+                    cur = nxt;
+                    i0 = i1;
+                }
             }
         }
     }
-    if (it > 0) settle(s + (it - 1) * a.nsplit, ((it - 1) & 1) ? lut1_s : lut0_s);
+    if (it > 0) settle(s + (it - 1) * a.nsplit, ((it - 1) & 1) ? lut1_s : lut0_s, last_seg0);
 
     // ---- final phase: shrink to the error band, evaluate the survivors exactly, exact top-k ----
     __syncthreads();

@@ -243,6 +243,7 @@ struct mmidx_index {
     std::vector<int32_t> shard_map;  // optional list -> owning shard (default l % shard_count)
     bool fast_ready = false;
     bool fast_len_ok = true;   // every list shorter than 2^22 entries (packed payload of the fp32 collector)
+    bool long_lists = false;   // some list exceeds FAST_SEG entries: segmented sweeps (k_ivfpq_scan_fast LONG)
     bool fast_range_ok = true;    // quantizer magnitudes inside the fp32-safe window (fast_scan.cuh); else exact kernels
     bool coarse_range_ok = true;  // same for the fp32 coarse filter (coarse_fast.cuh)
     bool force_exact = false;  // MMIDX_MODE=exact
@@ -251,8 +252,10 @@ struct mmidx_index {
     int sm_count = 148;        // SMs of this device: grids are sized in CTA slots = sm_count x resident CTAs per SM
     uint64_t gen = 0;          // bumped by everything that invalidates captured search graphs
     bool use_graph = true;     // MMIDX_GRAPH=0: always enqueue kernel by kernel
-    std::map<struct GraphKey, struct GraphEntry> *graphs = nullptr;
-    std::mutex graph_mu;
+    std::map<cudaStream_t, struct GraphCache *> graphs;  // captured search calls, per launching stream
+    std::mutex graph_mu;                                 // guards the map itself; every cache has its own lock
+    std::map<std::thread::id, cudaStream_t> thread_streams;  // mmidx_search: one stream per calling host thread
+    std::mutex ts_mu;
     std::vector<cudaEvent_t> ev_pool;  // mmidx_search's pipeline events, re-used across calls
     std::mutex ev_mu;
     struct Comm *comm = nullptr;       // multi-GPU exchange (mmidx_comm_*)
@@ -407,6 +410,9 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
         }
         cudaDeviceSynchronize();
         drop_graphs(ix);
+        for (auto &kv : ix->graphs) delete kv.second;
+        ix->graphs.clear();
+        for (auto &kv : ix->thread_streams) cudaStreamDestroy(kv.second);
         for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
         comm_release(ix);
         for (auto &kv : ix->arenas)
@@ -949,6 +955,9 @@ static int seal(mmidx_index *ix) {
         RET(post_launch("k_apply_order", nullptr));
         CK(cudaStreamSynchronize(st));
     }
+    ix->long_lists = false;
+    for (int32_t len : ix->h_list_len)
+        if (len > FAST_SEG) ix->long_lists = true;
     ix->sealed = true;
     return MMIDX_OK;
 }
@@ -1518,6 +1527,9 @@ static int seal_pq_fast(mmidx_index *ix) {
         RET(post_launch("k_apply_order", nullptr));
         CK(cudaStreamSynchronize(st));
     }
+    ix->long_lists = false;
+    for (int32_t len : ix->h_list_len)
+        if (len > FAST_SEG) ix->long_lists = true;
     ix->sealed = true;
     return MMIDX_OK;
 }
@@ -1636,7 +1648,9 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     RET(sc.get(&a.fb_count, 1));
     CK(cudaMemsetAsync(a.fb_count, 0, sizeof(int32_t), st));
     const size_t smem = fast_smem_bytes<CAP32, M>(ix->p.ks, ix->S, ix->p.d);
-    RET(set_smem(k_ivfpq_scan_fast<CAP32, M>, smem));
+    // lists longer than FAST_SEG entries (pseudo lists of a large flat PQ index) take the segmented sweep
+    auto scan_kernel = ix->long_lists ? k_ivfpq_scan_fast<CAP32, M, true> : k_ivfpq_scan_fast<CAP32, M, false>;
+    RET(set_smem(scan_kernel, smem));
     TopkOut o{};
     o.nparts = nsplit;
     if (nsplit == 1) {
@@ -1659,7 +1673,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     }
     {
         StageMark sm(ix, st, 2);
-        k_ivfpq_scan_fast<CAP32, M><<<dim3(nsplit, (unsigned)nq), MMIDX_NT, smem, st>>>(a, o);
+        scan_kernel<<<dim3(nsplit, (unsigned)nq), MMIDX_NT, smem, st>>>(a, o);
         RET(post_launch("k_ivfpq_scan_fast", launches));
     }
     StageMark sm3(ix, st, 3);
@@ -1871,13 +1885,41 @@ struct GraphEntry {
     uint64_t gen = 0, arena_gen = 0;
 };
 
-static void drop_graphs(mmidx_index *ix) {
-    if (!ix->graphs) return;
-    for (auto &kv : *ix->graphs)
+struct GraphCache {
+    std::mutex mu;  // held for a whole call: calls on one stream are serialised anyway, calls on different streams are not
+    std::map<GraphKey, GraphEntry> m;
+};
+
+static void clear_cache(GraphCache &c) {
+    for (auto &kv : c.m)
         for (auto &e : kv.second.exec)
             if (e) cudaGraphExecDestroy(e);
-    delete ix->graphs;
-    ix->graphs = nullptr;
+    c.m.clear();
+}
+
+static void drop_graphs(mmidx_index *ix) {
+    std::lock_guard<std::mutex> lk(ix->graph_mu);
+    for (auto &kv : ix->graphs) {
+        std::lock_guard<std::mutex> lk2(kv.second->mu);
+        clear_cache(*kv.second);
+    }
+}
+
+// The stream a host-pointer search call of this thread runs on.  One stream per calling thread: concurrent
+// computeNearestNeighbors callers (the reference leaves search unsynchronised, ASS.java:281) do not serialise on one stream,
+// and a thread's CUDA-graph capture never sees another thread's work on its stream.
+static int host_stream(mmidx_index *ix, cudaStream_t *out) {
+    std::lock_guard<std::mutex> lk(ix->ts_mu);
+    auto it = ix->thread_streams.find(std::this_thread::get_id());
+    if (it != ix->thread_streams.end()) {
+        *out = it->second;
+        return MMIDX_OK;
+    }
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    ix->thread_streams[std::this_thread::get_id()] = st;
+    *out = st;
+    return MMIDX_OK;
 }
 
 // enqueue(int *launches) issues the call on `st`; run_graphed decides between eager issue, capture and replay
@@ -1889,14 +1931,17 @@ static int run_graphed(mmidx_index *ix, GraphKey key, int parity, cudaStream_t s
         ix->last_launches = launches;
         return MMIDX_OK;
     }
-    std::lock_guard<std::mutex> lk(ix->graph_mu);
-    if (!ix->graphs) ix->graphs = new std::map<GraphKey, GraphEntry>();
-    if (ix->graphs->size() > 64) {  // callers that never repeat a shape: do not accumulate
-        drop_graphs(ix);
-        ix->graphs = new std::map<GraphKey, GraphEntry>();
+    GraphCache *cache;
+    {
+        std::lock_guard<std::mutex> lk0(ix->graph_mu);
+        GraphCache *&slot = ix->graphs[st];
+        if (!slot) slot = new GraphCache();
+        cache = slot;
     }
+    std::lock_guard<std::mutex> lk(cache->mu);
+    if (cache->m.size() > 64) clear_cache(*cache);  // callers that never repeat a shape: do not accumulate
     key.flags = (key.flags << 1) | (ix->timer.enabled ? 1 : 0);
-    GraphEntry &e = (*ix->graphs)[key];
+    GraphEntry &e = cache->m[key];
     uint64_t agen = 0, spills0 = 0;
     {
         std::lock_guard<std::mutex> lk2(ix->arena_mu);
@@ -2135,7 +2180,8 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
     RET(validate_search(ix, nq, k, &w));
     if (nq == 0) return MMIDX_OK;
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st;
+    RET(host_stream(ix, &st));
     Scratch sc(st, ix->arenas, ix->arena_mu);
     double *dQ, *ddist;
     int32_t *diids, *dcnt;
@@ -2518,10 +2564,7 @@ extern "C" int mmidx_comm_destroy(mmidx_t *ix) {
     DeviceGuard g(ix->device);
     cudaDeviceSynchronize();
     std::lock_guard<std::mutex> lk(ix->mu);
-    {
-        std::lock_guard<std::mutex> lk2(ix->graph_mu);
-        drop_graphs(ix);
-    }
+    drop_graphs(ix);
     comm_release(ix);
     ix->gen++;
     return MMIDX_OK;

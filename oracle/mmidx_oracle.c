@@ -187,6 +187,10 @@ void orc_set_rotation(const double *R, int d) {
     g_rot_d = d;
 }
 
+/* BASELINE.md variant (A): pay the reference's per-candidate allocations in orc_ivfpq_search (timing only) */
+static int g_faithful_costs = 0;
+void orc_set_faithful_costs(int on) { g_faithful_costs = on; }
+
 /* RandomPermutation.permute RandomPermutation.java:50-56: permuted[i] = vector[perm[i]] */
 static void apply_perm(const int32_t *perm, const double *v, int d, double *out) {
     if (g_rot && g_rot_d == d) {
@@ -331,6 +335,7 @@ int orc_ivfpq_search(const double *C, int nlist, int d, const double *P, int m, 
     double *v = (double *)malloc(sizeof(double) * (size_t)d);
     double *lut = (double *)malloc(sizeof(double) * (size_t)m * ks);
     orc_coarse_topw(C, nlist, d, q, w, probes);
+    const int cbytes = ks <= 256 ? m : 2 * m;
     for (int i = 0; i < w; i++) {
         int l = probes[i];
         const double *c = C + (int64_t)l * d;
@@ -340,6 +345,25 @@ int orc_ivfpq_search(const double *C, int nlist, int d, const double *P, int m, 
         for (int64_t pos = list_off[l]; pos < list_off[l + 1]; pos++) {
             double l2 = 0;
             int64_t start = pos * m;
+            if (g_faithful_costs) {
+                /* the reference's cost structure per candidate: pqByteCodes[l].toArray(start, m) copies the code into a
+                 * fresh array (IVFPQ.java:434), `new Result(iid, dist)` (:443-444), and an accepted offer allocates a
+                 * TreeSet entry while the evicted one becomes garbage.  Same arithmetic, same result. */
+                unsigned char *copy = (unsigned char *)malloc((size_t)cbytes);
+                memcpy(copy, (const unsigned char *)codes + pos * cbytes, (size_t)cbytes);
+                for (int j = 0; j < m; j++) l2 += lut[(int64_t)j * ks + code_at(copy, ks, j)];
+                volatile double *res = (volatile double *)malloc(2 * sizeof(double));
+                res[0] = (double)iids[pos];
+                res[1] = l2;
+                if (orc_bpq_offer(nn, iids[pos], res[1])) {
+                    void *node = malloc(48);
+                    *(volatile char *)node = 0;
+                    free(node);
+                }
+                free((void *)res);
+                free(copy);
+                continue;
+            }
             for (int j = 0; j < m; j++) l2 += lut[(int64_t)j * ks + code_at(codes, ks, start + j)];
             orc_bpq_offer(nn, iids[pos], l2);
         }

@@ -74,6 +74,9 @@ void orc_vlad(const double *codebook, int K, int D, const double *desc, int64_t 
  * encode / search functions apply instead of `perm` */
 void orc_apply_rotation(const double *R, int d, const double *v, double *out);
 void orc_set_rotation(const double *R, int d);
+/* BASELINE.md variant (A) of the CPU baseline: orc_ivfpq_search additionally pays the reference's per-candidate
+ * allocations (code copy IVFPQ.java:434, `new Result` :443-444, queue entry per accepted offer).  Results unchanged. */
+void orc_set_faithful_costs(int on);
 /* PCA.sampleToEigenSpace PCA.java:188-208 */
 void orc_pca_project(const double *Vt, const double *means, int nc, int ss, const double *x, int l2, double *out);
 void orc_normalize_l2(double *v, int64_t n);

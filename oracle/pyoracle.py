@@ -232,3 +232,8 @@ def vlad_multi(codebooks, desc, offsets, normalize=True, threads=1):
     if normalize and len(codebooks) > 1:
         multi = np.stack([normalize_l2(r) for r in multi])
     return multi
+
+
+def set_faithful_costs(on):
+    """BASELINE.md variant (A): ivfpq_search pays the reference's per-candidate allocations (timing runs only)"""
+    lib.orc_set_faithful_costs(1 if on else 0)
