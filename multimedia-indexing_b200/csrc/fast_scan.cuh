@@ -805,10 +805,12 @@ __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t
 }
 
 // grid (nsplit, nq).  CTA (s, q) handles owned probe slots s, s+nsplit, ... of query q in rank order.
-// Shared memory: TopK32 | t2 | stage (TMA target: T1 row of the next probe) | lut[2] | qv.
-// Per probe: one independent descriptor load, the fp32 table lut = (T1[l] + T2) + s built with 128-bit shared accesses
-// into the buffer the previous probe is not using, ONE block barrier (which also settles the collector), the TMA for
-// the next T1 row, then a barrier-free sweep over the list with the next 128-bit code load in flight.
+// Shared memory: TopK32 | t2 | lut[2] | qv.
+// Per probe: one independent descriptor load, wait for the TMA of the probe's T1 row -- it lands straight in the table
+// buffer the previous probe is not using -- then the fp32 table lut = (T1[l] + T2) + s is built IN PLACE with 128-bit shared
+// accesses, ONE block barrier (which also settles the collector), the TMA of the next T1 row into the other buffer (its
+// last reader, the previous probe's sweep, ended at that barrier), then a barrier-free sweep over the list with the next
+// 128-bit code load in flight.  (No staging buffer: 33 KB per CTA at m = 8, 66 KB at m = 16 -- three CTAs per SM instead of two.)
 // LONG: some list is longer than FAST_SEG entries (the pseudo lists of a large flat PQ index: 10^5 entries).  Such lists are
 // swept in segments of FAST_SEG entries with a settle in between, so that the admission threshold is re-read while it
 // tightens and a collector overflow re-scans one segment, not the list (without this a 1 GiB flat scan ran at 25 % of the
@@ -829,17 +831,16 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TopK32<CAP32> &c32 = *reinterpret_cast<TopK32<CAP32> *>(smem_raw);
     const size_t c32_bytes = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
-    // region A (scan phase): t2 | stage | lut0 | lut1.   Aliased in the final phase by: TopK<ECAP> | s_l | xs
+    // region A (scan phase): t2 | lut0 | lut1.   Aliased in the final phase by: TopK<ECAP> | s_l | xs
     unsigned char *regA = smem_raw + c32_bytes;
     float *t2 = reinterpret_cast<float *>(regA);   // [nent]
-    float *stage = t2 + nent;                      // [nent]
-    float *lut0 = stage + nent;                    // [nent]
-    float *lut1 = lut0 + nent;                     // [nent]
+    float *lut0 = t2 + nent;                       // [nent]  TMA target of the even probes, table built in place
+    float *lut1 = lut0 + nent;                     // [nent]  ... of the odd probes
     const uint32_t lut0_s = smem_u32(lut0), lut1_s = smem_u32(lut1);
     const size_t tk_bytes = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
     // final phase needs room for at least one survivor's terms (host: fast_smem_bytes)
     const size_t fin_bytes = tk_bytes + ECAP * sizeof(int) + (size_t)M * (a.S + 1) * sizeof(double);
-    const size_t regA_bytes = max((size_t)4 * nent * sizeof(float), fin_bytes);
+    const size_t regA_bytes = max((size_t)3 * nent * sizeof(float), fin_bytes);
     double *qv = reinterpret_cast<double *>(regA + ((regA_bytes + 15) & ~(size_t)15));  // [d] raw query
     uint64_t *bars = reinterpret_cast<uint64_t *>(qv + a.d);                            // [1]
 
@@ -865,12 +866,11 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     if (tid == 0 && s < nop) {
         const int l0 = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)s * DSTRIDE)->l;
         mbar_arrive_expect_tx(&bars[0], t1_bytes);
-        tma_load_1d(stage, a.T1 + (int64_t)l0 * nent, t1_bytes, &bars[0]);
+        tma_load_1d(lut0, a.T1 + (int64_t)l0 * nent, t1_bytes, &bars[0]);
     }
     // ---- per-query prologue: this query's T2 row (k_fast_t2) into shared memory.  Thread tid owns the float4
     //      entries tid + 256*r of every table (t2, stage, lut): it only ever re-reads what it wrote itself. ----
     float4 *t2v = reinterpret_cast<float4 *>(t2);
-    const float4 *stv = reinterpret_cast<const float4 *>(stage);
     {
         const float4 *t2g = reinterpret_cast<const float4 *>(a.T2 + q * (int64_t)nent);
 #pragma unroll
@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
 #pragma unroll
             for (int r = 0; r < NV; ++r) {
                 const int e4 = tid + MMIDX_NT * r;
-                const float4 sv = stv[e4], tv = t2v[e4];
+                const float4 sv = lutv[e4], tv = t2v[e4];  // sv: the T1 row the TMA delivered into this buffer
                 float4 ov;
                 ov.x = (sv.x + tv.x) + sj[r];
                 ov.y = (sv.y + tv.y) + sj[r];
@@ -938,10 +938,11 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
         // the probe's barrier: publishes the table, ends every read of `stage` and every push of the previous list
         settle(ii - a.nsplit, (it & 1) ? lut0_s : lut1_s, last_seg0);
         if (tid == 0 && ii + a.nsplit < nop) {
-            // every thread has consumed `stage`: the next probe's T1 row lands while this list is scanned
+            // the other buffer's last readers (the previous probe's sweep and its possible re-scan in settle) are done:
+            // the next probe's T1 row lands there while this list is scanned
             fence_proxy_async();
             mbar_arrive_expect_tx(&bars[0], t1_bytes);
-            tma_load_1d(stage, a.T1 + (int64_t)lnext * nent, t1_bytes, &bars[0]);
+            tma_load_1d((it & 1) ? lut0 : lut1, a.T1 + (int64_t)lnext * nent, t1_bytes, &bars[0]);
         }
         const unsigned int ltag = ((unsigned int)ii) << FAST_POS_BITS;
         const uint8_t *list_codes = lc;

@@ -29,6 +29,7 @@
 #include "fast_scan.cuh"
 #include "comm.cuh"
 #include "aux_ops.cuh"
+#include "argmin_filter.cuh"
 
 using namespace mmidx;
 
@@ -237,6 +238,7 @@ struct mmidx_index {
     int flat_nlist = 0;       // ... and its pseudo lists of equal length
     DevBuf dC32, dc2, dcmax;  // coarse_fast.cuh: fp32 copy of the coarse quantizer, ||C||^2, max ||C||
     DevBuf dCh, dCl;          // ... and its bf16 hi / lo split for the tensor-core filter (k_coarse_mma)
+    DevBuf dPf32, dPb2, dPbmax;  // argmin_filter.cuh: fp32 product codebooks [m][ks][S], ||P_j,c||^2, max norm per sub-quantizer
     int dpad = 0;             // d rounded up to 16
     bool coarse_mma_ok = false;   // the tensor-core filter passed its measurement against binary64 on this quantizer
     double coarse_mma_measured = 0.0;  // measured error coefficient (of ||q|| Cmax), for mmidx_debug / logs
@@ -451,6 +453,17 @@ extern "C" int mmidx_set_product_quantizer(mmidx_t *ix, const double *P) {
     size_t bytes = sizeof(double) * (size_t)ix->p.m * ix->p.ks * ix->S;
     RET(ix->dP.reserve(bytes, 0, ix->stream));
     CK(cudaMemcpyAsync(ix->dP.p, P, bytes, cudaMemcpyHostToDevice, ix->stream));
+    {
+        // fp32 tables of the encode filter (argmin_filter.cuh)
+        const int m = ix->p.m, ks = ix->p.ks, S = ix->S;
+        RET(ix->dPf32.reserve(sizeof(float) * (size_t)m * ks * S, 0, ix->stream));
+        RET(ix->dPb2.reserve(sizeof(float) * (size_t)m * ks, 0, ix->stream));
+        RET(ix->dPbmax.reserve(sizeof(float) * (size_t)m, 0, ix->stream));
+        CK(cudaMemsetAsync(ix->dPbmax.p, 0, sizeof(float) * (size_t)m, ix->stream));
+        k_argmin_tables<<<dim3(ks, m), MMIDX_NT, 0, ix->stream>>>(ix->dP.as<double>(), ks, S, ix->dPf32.as<float>(), ix->dPb2.as<float>(),
+                                                                 ix->dPbmax.as<float>());
+        RET(post_launch("k_argmin_tables", nullptr));
+    }
     CK(cudaStreamSynchronize(ix->stream));
     ix->has_P = true;
     ix->fast_ready = false;
@@ -616,6 +629,57 @@ static int launch_assign(const double *dA, const double *dBt, int64_t na, int nb
     return post_launch("k_assign_nearest", launches);
 }
 
+static bool env_exact() {
+    static const bool v = [] {
+        const char *e = getenv("MMIDX_MODE");
+        return e && strcmp(e, "exact") == 0;
+    }();
+    return v;
+}
+
+// IVFPQ.computeNearestCoarseIndex (IVFPQ.java:547-564) for n vectors: filter matrix on the tensor cores (or FFMA), row minimum
+// with the filter's error radius, binary64 only for the vectors the filter cannot decide (argmin_filter.cuh)
+static int coarse_assign_dev(mmidx_index *ix, const double *dX, int64_t n, int32_t *dlist, cudaStream_t st, int *launches, Scratch &sc) {
+    const int nlist = ix->p.nlist, d = ix->p.d;
+    if (ix->force_exact || !ix->coarse_range_ok)
+        return launch_assign(dX, ix->dCt.as<double>(), n, nlist, d, dlist, st, launches);
+    const int64_t QC = std::max<int64_t>(1, (int64_t)(((size_t)512 << 20) / ((size_t)nlist * sizeof(float))));
+    const int64_t cb = std::min(QC, n);
+    float *A32;
+    int64_t *amb_list;
+    int32_t *amb_count;
+    RET(sc.get(&A32, (size_t)cb * nlist));
+    RET(sc.get(&amb_list, (size_t)cb));
+    RET(sc.get(&amb_count, 1));
+    for (int64_t q0 = 0; q0 < n; q0 += cb) {
+        const int64_t nb = std::min(cb, n - q0);
+        const double *xq = dX + q0 * d;
+        double coef;
+        if (ix->coarse_mma_ok) {
+            RET(set_smem(k_coarse_mma, TM_SMEM));
+            dim3 gg((unsigned)((nlist + TM_BN - 1) / TM_BN), (unsigned)((nb + TM_BM - 1) / TM_BM));
+            k_coarse_mma<<<gg, MMIDX_NT, TM_SMEM, st>>>(xq, ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>(), ix->dc2.as<float>(),
+                                                        nb, nlist, d, ix->dpad, A32);
+            RET(post_launch("k_coarse_mma", launches));
+            coef = coarse_coef_mma(d);
+        } else {
+            dim3 gg((unsigned)((nlist + CG_BN - 1) / CG_BN), (unsigned)((nb + CG_BM - 1) / CG_BM));
+            k_coarse_f32<<<gg, MMIDX_NT, 0, st>>>(xq, ix->dC32.as<float>(), ix->dc2.as<float>(), nb, nlist, d, A32);
+            RET(post_launch("k_coarse_f32", launches));
+            coef = coarse_coef_ffma(d);
+        }
+        CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+        k_rowmin_filter<<<(unsigned)((nb * 32 + MMIDX_NT - 1) / MMIDX_NT), MMIDX_NT, 0, st>>>(A32, xq, nb, nlist, d, ix->dcmax.as<float>(), coef,
+                                                                                                dlist + q0, amb_list, amb_count);
+        RET(post_launch("k_rowmin_filter", launches));
+        ArgminRows rows{xq, d, nullptr, nullptr, 0, nullptr, 0};
+        k_argmin_exact_list<<<2 * ix->sm_count, MMIDX_NT, 0, st>>>(rows, ix->dC.as<double>(), nlist, d, 1, amb_list, amb_count, nullptr, nullptr,
+                                                                   dlist + q0, 1);
+        RET(post_launch("k_argmin_exact_list", launches));
+    }
+    return MMIDX_OK;
+}
+
 static int launch_pq_encode(mmidx_index *ix, const double *dX, const int32_t *dlist, int64_t n, uint8_t *dout,
                             cudaStream_t st, int *launches, Scratch &sc) {
     if (n == 0) return MMIDX_OK;
@@ -632,6 +696,23 @@ static int launch_pq_encode(mmidx_index *ix, const double *dX, const int32_t *dl
         C = nullptr;
         dlist = nullptr;
         perm = nullptr;
+    }
+    if (!ix->force_exact) {
+        // fp32 filter per sub-quantizer; binary64 only for the (vector, sub-quantizer) pairs it cannot decide
+        int64_t *amb_list;
+        int32_t *amb_count;
+        RET(sc.get(&amb_list, (size_t)n * m));
+        RET(sc.get(&amb_count, 1));
+        CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+        ArgminRows rows{dX, d, C, dlist, d, perm, 0};
+        uint8_t *o8 = ks <= 256 ? dout : nullptr;
+        uint16_t *o16 = ks <= 256 ? nullptr : reinterpret_cast<uint16_t *>(dout);
+        dim3 gf((unsigned)((n + AF_TV - 1) / AF_TV), m);
+        k_argmin_filter<<<gf, MMIDX_NT, 0, st>>>(rows, ix->dPf32.as<float>(), ix->dPb2.as<float>(), ix->dPbmax.as<float>(), n, ks, S, m, o8, o16,
+                                                 nullptr, m, amb_list, amb_count);
+        RET(post_launch("k_argmin_filter", launches));
+        k_argmin_exact_list<<<2 * ix->sm_count, MMIDX_NT, 0, st>>>(rows, ix->dP.as<double>(), ks, S, m, amb_list, amb_count, o8, o16, nullptr, m);
+        return post_launch("k_argmin_exact_list", launches);
     }
     const double *P = ix->dP.as<double>();
     dim3 grid((unsigned)((n + MMIDX_NT - 1) / MMIDX_NT), m);
@@ -654,7 +735,7 @@ static int launch_pq_encode(mmidx_index *ix, const double *dX, const int32_t *dl
 static int encode_dev(mmidx_index *ix, const double *dX, int64_t n, int32_t *dlist, uint8_t *dcodes, cudaStream_t st,
                       int *launches, Scratch &sc) {
     if (ix->p.type == MMIDX_IVFPQ) {
-        RET(launch_assign(dX, ix->dCt.as<double>(), n, ix->p.nlist, ix->p.d, dlist, st, launches));
+        RET(coarse_assign_dev(ix, dX, n, dlist, st, launches, sc));
         RET(launch_pq_encode(ix, dX, dlist, n, dcodes, st, launches, sc));
     } else {
         RET(launch_pq_encode(ix, dX, nullptr, n, dcodes, st, launches, sc));
@@ -740,6 +821,14 @@ static int add_or_encode(mmidx_index *ix, int64_t n, const double *X, int32_t *o
     if (ix->shard_count > 1) RET(sc.get(&dsel, (size_t)bmax));
     std::vector<int32_t> hl;
     std::vector<int64_t> hsel;
+    if (store) {
+        // one growth step for the whole call (a shard keeps at most all n): no re-allocation inside the batch loop
+        RET(ix->dcodes.reserve((size_t)(ix->n_local + n) * cb, (size_t)ix->n_local * cb, st));
+        if (ix->p.type == MMIDX_IVFPQ) {
+            ix->h_list.reserve(ix->h_list.size() + (size_t)n);
+            ix->h_iid.reserve(ix->h_iid.size() + (size_t)n);
+        }
+    }
     for (int64_t b = 0; b < n; b += ADD_BATCH) {
         int64_t nb = std::min(ADD_BATCH, n - b);
         const double *xb = X + b * d;
@@ -1551,7 +1640,7 @@ static size_t fast_smem_bytes(int ks, int S, int d) {
     const size_t c32b = (sizeof(TopK32<CAP32>) + 127) & ~(size_t)127;
     const size_t tkb = (sizeof(TopK<ECAP>) + 127) & ~(size_t)127;
     const size_t finb = tkb + ECAP * sizeof(int) + (size_t)M * (S + 1) * sizeof(double);  // final phase of k_ivfpq_scan_fast
-    size_t regA = std::max((size_t)4 * M * ks * sizeof(float), finb);
+    size_t regA = std::max((size_t)3 * M * ks * sizeof(float), finb);
     regA = (regA + 15) & ~(size_t)15;
     return c32b + regA + (size_t)d * 8 + 16 + 64;
 }
@@ -2830,9 +2919,38 @@ static int vlad_dev_impl(const double *d_codebook, int32_t K, int32_t D, int64_t
     if (!assign) RET(sc.get(&assign, (size_t)n_desc));
     RET(sc.get(&order, (size_t)n_desc));
     RET(sc.get(&cstart, (size_t)n_img * (K + 1)));
-    k_transpose<<<(unsigned)(((size_t)K * D + 255) / 256), 256, 0, st>>>(d_codebook, K, D, dBt);
-    RET(post_launch("k_transpose", nullptr));
-    RET(launch_assign(d_desc, dBt, n_desc, K, D, assign, st, nullptr));
+    if (env_exact() || n_desc == 0) {
+        k_transpose<<<(unsigned)(((size_t)K * D + 255) / 256), 256, 0, st>>>(d_codebook, K, D, dBt);
+        RET(post_launch("k_transpose", nullptr));
+        RET(launch_assign(d_desc, dBt, n_desc, K, D, assign, st, nullptr));
+    } else {
+        // computeNearestCentroid through the fp32 filter (argmin_filter.cuh): tables of this codebook, filter, exact leftovers
+        float *B32, *b2, *bmax;
+        int64_t *amb_list;
+        int32_t *amb_count;
+        RET(sc.get(&B32, (size_t)K * D));
+        RET(sc.get(&b2, (size_t)K));
+        RET(sc.get(&bmax, 1));
+        RET(sc.get(&amb_list, (size_t)n_desc));
+        RET(sc.get(&amb_count, 1));
+        CK(cudaMemsetAsync(bmax, 0, sizeof(float), st));
+        CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+        k_argmin_tables<<<dim3(K, 1), MMIDX_NT, 0, st>>>(d_codebook, K, D, B32, b2, bmax);
+        RET(post_launch("k_argmin_tables", nullptr));
+        ArgminRows rows{d_desc, D, nullptr, nullptr, 0, nullptr, 0};
+        for (int64_t v0 = 0; v0 < n_desc; v0 += (int64_t)AF_TV * 2000000) {  // grid.x limit
+            const int64_t nb = std::min<int64_t>((int64_t)AF_TV * 2000000, n_desc - v0);
+            ArgminRows rc = rows;
+            rc.X = d_desc + v0 * D;
+            k_argmin_filter<<<dim3((unsigned)((nb + AF_TV - 1) / AF_TV), 1), MMIDX_NT, 0, st>>>(rc, B32, b2, bmax, nb, K, D, 1, nullptr, nullptr,
+                                                                                              assign + v0, 1, amb_list, amb_count);
+            RET(post_launch("k_argmin_filter", nullptr));
+            k_argmin_exact_list<<<2 * current_sm_count(), MMIDX_NT, 0, st>>>(rc, d_codebook, K, D, 1, amb_list, amb_count, nullptr, nullptr,
+                                                                             assign + v0, 1);
+            RET(post_launch("k_argmin_exact_list", nullptr));
+            if (v0 + nb < n_desc) CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+        }
+    }
     size_t smem = sizeof(int) * (size_t)(K + 1);
     if (smem > 48 * 1024) RET(set_smem(k_vlad_order, smem));
     for (int64_t i0 = 0; i0 < n_img; i0 += 1 << 30) {

@@ -641,3 +641,47 @@ def test_random_rotation_with_a_supplied_matrix(kind):
             assert_same(pq.searchBatch(k, Q), O.pq_search(P, oc, Q, k, threads=1), "rotated pq")
     finally:
         O.set_rotation(None)
+
+
+def test_filtered_argmins_resolve_ties_like_the_reference():
+    """argmin_filter.cuh: nearest product centroid (PQ.java:411-429), nearest coarse centroid (IVFPQ.java:547-564) and nearest
+    VLAD centroid (AFA.java:136-155) are decided by an fp32 filter when the runner-up is provably farther and in binary64
+    otherwise.  Duplicated centroids and vectors that sit exactly on centroids / midway between two force the binary64 path:
+    the lowest index among equal minima must win, as the reference's strict `<` does."""
+    rng = np.random.default_rng(11)
+    d, m, ks, nlist, n = 64, 8, 256, 40, 5000
+    S = d // m
+    ce = synth.mixture_centers(d, 32)
+    X = synth.mixture(n, d, synth.SEED_DB, ce)
+    Cq = synth.kmeans(X[:2000], nlist, 2, seed=3)
+    Cq[7] = Cq[3]          # duplicated coarse centroids: list 3 must win over list 7
+    Cq[39] = Cq[0]
+    P = synth.train_pq_on(Cq[synth._assign(X[:2000], Cq)] - X[:2000], m, ks, iters=2)
+    P[:, 200] = P[:, 5]    # duplicated product centroids in every sub-quantizer
+    P[2, 17] = P[2, 16]
+    X[:50] = Cq[rng.integers(0, nlist, 50)]                       # vectors ON coarse centroids (residual 0)
+    X[50:100] = 0.5 * (Cq[rng.integers(0, nlist, 50)] + Cq[rng.integers(0, nlist, 50)])  # midway between two
+    X[100:150] = Cq[3] - P[:, 5].reshape(-1)                      # residual exactly the duplicated product centroid
+    ix = make_ivfpq(d, m, ks, nlist, 8, Cq, P)
+    lists, codes = ix.indexVectors(None, X, return_codes=True)
+    ol, oc = O.ivfpq_encode(Cq, P, X, threads=8)
+    assert (lists == ol).all() and (codes == oc).all()
+    assert not (lists == 7).any() and not (codes == 200).any()    # the later duplicate never wins
+    pq = M.PQ(d, n, m, ks)
+    pq.loadProductQuantizer(P)
+    Y = X.copy()
+    Y[:200] = np.tile(P[:, rng.integers(0, ks, 200)].transpose(1, 0, 2).reshape(200, d), 1)  # vectors made of product centroids
+    _, pc = pq.indexVectors(None, Y, return_codes=True)
+    assert (pc == O.pq_encode(P, Y, threads=8)).all()
+    # VLAD assignment with duplicated codebook rows and descriptors on / between centroids
+    K, D = 64, 32
+    desc, offs = synth.descriptors(30, D)
+    cb = synth.kmeans(desc[:5000], K, 2, seed=2)
+    cb[40] = cb[9]
+    desc[:64] = cb
+    desc[64:100] = 0.5 * (cb[:36] + cb[1:37])
+    agg = M.VladAggregator(cb)
+    out, assign = agg.aggregateBatch((desc, offs), return_assign=True)
+    ov, oa = O.vlad(cb, desc, offs, threads=8)
+    assert (assign == oa).all() and (out == ov.reshape(out.shape)).all()
+    assert not (assign == 40).any()
