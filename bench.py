@@ -259,7 +259,9 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
-        self.stream = torch.cuda.current_stream()
+        # a side stream is made torch's current one: the legacy default stream cannot be captured into a CUDA graph
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
         self.st = C.c_void_p(self.stream.cuda_stream)
 
     def barrier(self):
@@ -722,10 +724,11 @@ def run_gpu(args, rank, world, local_rank):
     scan_ms = float(stage_ms[2])
     achieved = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))["dram_bytes_per_step"]
-    except Exception:
-        pass
+    if world == 1:  # the committed ncu capture is of this exact launch (N = 1, 10 000 queries); not transferable to other N
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))["dram_bytes_per_step"]
+        except Exception:
+            pass
     roof = {"bound": "hbm", "kernel": "k_ivfpq_scan_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms_per_launch": scan_ms,

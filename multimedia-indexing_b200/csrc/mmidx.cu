@@ -2015,7 +2015,8 @@ static int host_stream(mmidx_index *ix, cudaStream_t *out) {
 template <typename F>
 static int run_graphed(mmidx_index *ix, GraphKey key, int parity, cudaStream_t st, F enqueue) {
     int launches = 0;
-    if (!ix->use_graph) {
+    // the legacy default stream (what a caller passes as stream 0) and the per-thread default stream cannot be captured
+    if (!ix->use_graph || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
         RET(enqueue(&launches));
         ix->last_launches = launches;
         return MMIDX_OK;

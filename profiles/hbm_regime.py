@@ -35,6 +35,7 @@ for b in range(0, args.n, 1 << 24):
     codes = rng.integers(0, 256, size=(nb, m), dtype=np.uint8)
     check(lib.mmidx_add_codes(pq._h, nb, None, C.c_void_p(codes.ctypes.data)))
 dev = torch.device("cuda", 0)
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # capturable (the legacy default stream is not)
 Q = torch.from_numpy(rng.normal(64, 20, size=(args.nq, d))).to(dev)
 ii = torch.empty((args.nq, k), dtype=torch.int32, device=dev)
 dd = torch.empty((args.nq, k), dtype=torch.float64, device=dev)

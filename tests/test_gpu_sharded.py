@@ -58,6 +58,7 @@ def _worker(rank, world, port, q):
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        torch.cuda.set_stream(torch.cuda.Stream())  # a capturable stream: steps 3+ of every case replay CUDA graphs
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         for p in (root, os.path.join(root, "oracle")):
             sys.path.insert(0, p)
@@ -90,7 +91,7 @@ def _worker(rank, world, port, q):
             mi.setW(w)
             lists, codes = mi.indexAll(X, balanced=(case != "plain"))
             mi.connect(max_gq=1024, k_max=128)
-            same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=4)
+            same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=7)
             same &= _check(mi, O, synth, Cq, P, lists, codes, nlist, Q[: nq // 2], k, w, gather=False, steps=2)
             ok &= bool(same)
             stored = int(mi.listSizes().sum())
@@ -120,7 +121,7 @@ def _worker(rank, world, port, q):
         mi.setW(w)
         lists, codes = mi.indexAll(X)
         mi.connect(max_gq=1024, k_max=100)
-        same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=4)
+        same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=7)
         ok &= bool(same)
         msgs.append(f"S=1 x R={world}: equal={bool(same)}")
         dist.barrier()
@@ -132,7 +133,7 @@ def _worker(rank, world, port, q):
             mi.setW(w)
             lists, codes = mi.indexAll(X)
             mi.connect(max_gq=1024, k_max=100)
-            same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=4)
+            same = _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=True, steps=7)
             same &= _check(mi, O, synth, Cq, P, lists, codes, nlist, Q, k, w, gather=False, steps=2)
             ok &= bool(same)
             msgs.append(f"S=2 x R={world // 2}: equal={bool(same)}")
@@ -191,10 +192,11 @@ def test_multi_step_on_one_gpu():
     mi.setW(w)
     lists, codes = mi.indexAll(X)
     mi.connect(max_gq=512, k_max=16)
+    torch.cuda.set_stream(torch.cuda.Stream())  # a capturable stream (the legacy default stream is not): steps 3+ replay graphs
     off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
     oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w)
     dQ = torch.from_numpy(Q).cuda()
-    for step in range(5):
+    for step in range(8):
         iids, dd, cnt, row0, nrows = mi.search(k, dQ, gather_all=True)
         torch.cuda.synchronize()
         assert (row0, nrows) == (0, nq)
