@@ -463,6 +463,10 @@ def other_rows(ctx, M, wl, synth, X, Q, ce, have_cpu):
         pq.loadProductQuantizer(Pf)
         dX = torch.from_numpy(X).to(ctx.dev)
         dcodes = torch.empty((wl["N_DB"], wl["M"]), dtype=torch.uint8, device=ctx.dev)
+        warm = M.PQ(wl["D"], 20_000, wl["M"], wl["KS"], M.TransformationType.None_, device=ctx.dev.index)  # loads the encode kernels
+        warm.loadProductQuantizer(Pf)
+        M._capi.check(lib.mmidx_add_dev(warm._h, 20_000, ptr(dX), None, ptr(dcodes)))
+        warm.close()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         M._capi.check(lib.mmidx_add_dev(pq._h, wl["N_DB"], ptr(dX), None, ptr(dcodes)))

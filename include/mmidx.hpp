@@ -110,6 +110,10 @@ protected:
     int64_t maxNumVectors;
     std::unordered_map<std::string, int> nameToId_;  // the reference's "nameToId" / "idToName" BDB databases
     std::vector<std::string> idToName_;
+    bool rotation_pending_ = false;  // PQ / IVFPQ built with RandomRotation wait for setRotation()
+    void require_ready() const {
+        if (rotation_pending_) throw Exception(MMIDX_ERR_UNSUPPORTED, "RandomRotation: supply the rotation matrix with setRotation() first");
+    }
 
     AbstractSearchStructure(int vectorLength_, int64_t maxNumVectors_) : vectorLength(vectorLength_), maxNumVectors(maxNumVectors_) {}
     void create(const mmidx_params &p) { check(mmidx_create(&p, &h_)); }
@@ -144,6 +148,7 @@ public:
         if ((int64_t)idToName_.size() >= maxNumVectors) return false;
         if (isIndexed(id)) return false;
         if ((int)vector.size() != vectorLength) throw Exception(MMIDX_ERR_DIM, "The dimensionality of the vector is wrong!");
+        require_ready();
         const int rc = mmidx_add(h_, 1, vector.data(), nullptr, nullptr);
         if (rc == MMIDX_ERR_FULL) return false;
         check(rc);
@@ -155,6 +160,7 @@ public:
     // ASS.java:281-291
     Answer computeNearestNeighbors(int k, const std::vector<double> &queryVector) {
         if ((int)queryVector.size() != vectorLength) throw Exception(MMIDX_ERR_DIM, "The dimensionality of the vector is wrong!");
+        require_ready();
         std::vector<int32_t> iids((size_t)(k > 0 ? k : 0));
         std::vector<double> dist(iids.size());
         int32_t cnt = 0;
@@ -211,8 +217,9 @@ protected:
         subVectorLength = vectorLength_ / m;
     }
     void set_transformation(TransformationType t, int seed) {
-        if (t == TransformationType::RandomRotation)  // EJML's generator is not reproducible offline
-            throw Exception(MMIDX_ERR_UNSUPPORTED, "RandomRotation needs the rotation matrix; use RandomPermutation or None");
+        // RandomRotation: EJML's generator is not reproducible offline; the constructor leaves the index
+        // untransformed until setRotation() supplies the matrix -- indexing before that would silently differ, so it throws
+        if (t == TransformationType::RandomRotation) rotation_pending_ = true;
         if (t == TransformationType::RandomPermutation) {
             const std::vector<int32_t> perm = random_permutation(seed, vectorLength);
             check(mmidx_set_permutation(h_, perm.data()));
@@ -220,6 +227,15 @@ protected:
     }
 
 public:
+    // TransformationType.RandomRotation with the d x d matrix of RandomRotation.java:30-35 supplied (row-major):
+    // transformed = v R, as RandomRotation.rotate (RandomRotation.java:44-49)
+    void setRotation(const std::vector<double> &R) {
+        if ((int64_t)R.size() != (int64_t)vectorLength * vectorLength) throw Exception(MMIDX_ERR_DIM, "the rotation matrix must be d x d");
+        check(mmidx_set_transform(h_, MMIDX_TRANSFORM_ROTATION, nullptr, R.data()));
+        rotation_pending_ = false;
+    }
+    bool rotationPending() const { return rotation_pending_; }
+
     // PQ.java:142-144 (without the BDB arguments); seed = 1 as in PQ.java:160
     PQ(int vectorLength_, int64_t maxNumVectors_, int numSubVectors_, int numProductCentroids_,
        TransformationType transformation = TransformationType::None, int device = -1)

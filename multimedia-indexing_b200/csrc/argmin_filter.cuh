@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_argmin_filter(ArgminRows rows, con
 __global__ void __launch_bounds__(MMIDX_NT) k_rowmin_filter(const float *__restrict__ A32, const double *__restrict__ X, int64_t n,
                                                             int K, int D, const float *__restrict__ cmax, double coef,
                                                             int32_t *__restrict__ out32, int64_t *__restrict__ amb_list,
-                                                            int32_t *__restrict__ amb_count) {
+                                                            float *__restrict__ amb_thr, int32_t *__restrict__ amb_count) {
     const int lane = threadIdx.x & 31;
     const int64_t v = ((int64_t)blockIdx.x * MMIDX_NT + threadIdx.x) >> 5;
     if (v >= n) return;
@@ -243,7 +243,50 @@ __global__ void __launch_bounds__(MMIDX_NT) k_rowmin_filter(const float *__restr
         } else {
             const int slot = atomicAdd(amb_count, 1);
             amb_list[slot] = v;
+            // every centroid that can still be the exact argmin has a <= a1 + 2R; outside the fp32-safe window: all of them
+            amb_thr[slot] = in_range ? __double2float_ru((double)m.a1 + 2.0 * R) : __int_as_float(0x7f800000);
         }
+    }
+}
+
+// the listed rows in binary64, but only over the centroids the filter could not exclude (a <= thr): typically two or three of
+// the K.  One warp per row; a lane that finds a candidate adds its D terms for t ascending (the reference's loop); strict `<`
+// and the (distance, index) merge keep the lowest index among equal minima.
+__global__ void __launch_bounds__(MMIDX_NT) k_rowmin_exact_list(const float *__restrict__ A32, const double *__restrict__ X,
+                                                                const double *__restrict__ B, int K, int D,
+                                                                const int64_t *__restrict__ amb_list, const float *__restrict__ amb_thr,
+                                                                const int32_t *__restrict__ amb_count, int32_t *__restrict__ out32) {
+    const int na = *amb_count;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * MMIDX_NT) >> 5;
+    for (int a = (blockIdx.x * MMIDX_NT + threadIdx.x) >> 5; a < na; a += warps) {
+        const int64_t v = amb_list[a];
+        const float thr = amb_thr[a];
+        const float *row = A32 + v * (int64_t)K;
+        const double *x = X + v * (int64_t)D;
+        double best = 1.7976931348623157e308;  // Double.MAX_VALUE
+        int bidx = 0x7fffffff;
+        const bool all = thr == __int_as_float(0x7f800000);  // outside the fp32-safe window the filter values mean nothing
+        for (int c = lane; c < K; c += 32) {
+            if (!all && !(row[c] <= thr)) continue;
+            const double *bc = B + (int64_t)c * D;
+            double acc = 0.0;
+            for (int t = 0; t < D; ++t) acc = sqacc(acc, bc[t], x[t]);
+            if (acc < best) {
+                best = acc;
+                bidx = c;
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, s);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, s);
+            if (ob < best || (ob == best && oi < bidx)) {
+                best = ob;
+                bidx = oi;
+            }
+        }
+        if (lane == 0) out32[v] = bidx == 0x7fffffff ? -1 : bidx;
     }
 }
 

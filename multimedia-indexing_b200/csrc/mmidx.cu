@@ -645,11 +645,12 @@ static int coarse_assign_dev(mmidx_index *ix, const double *dX, int64_t n, int32
         return launch_assign(dX, ix->dCt.as<double>(), n, nlist, d, dlist, st, launches);
     const int64_t QC = std::max<int64_t>(1, (int64_t)(((size_t)512 << 20) / ((size_t)nlist * sizeof(float))));
     const int64_t cb = std::min(QC, n);
-    float *A32;
+    float *A32, *amb_thr;
     int64_t *amb_list;
     int32_t *amb_count;
     RET(sc.get(&A32, (size_t)cb * nlist));
     RET(sc.get(&amb_list, (size_t)cb));
+    RET(sc.get(&amb_thr, (size_t)cb));
     RET(sc.get(&amb_count, 1));
     for (int64_t q0 = 0; q0 < n; q0 += cb) {
         const int64_t nb = std::min(cb, n - q0);
@@ -670,12 +671,10 @@ static int coarse_assign_dev(mmidx_index *ix, const double *dX, int64_t n, int32
         }
         CK(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
         k_rowmin_filter<<<(unsigned)((nb * 32 + MMIDX_NT - 1) / MMIDX_NT), MMIDX_NT, 0, st>>>(A32, xq, nb, nlist, d, ix->dcmax.as<float>(), coef,
-                                                                                                dlist + q0, amb_list, amb_count);
+                                                                                                dlist + q0, amb_list, amb_thr, amb_count);
         RET(post_launch("k_rowmin_filter", launches));
-        ArgminRows rows{xq, d, nullptr, nullptr, 0, nullptr, 0};
-        k_argmin_exact_list<<<2 * ix->sm_count, MMIDX_NT, 0, st>>>(rows, ix->dC.as<double>(), nlist, d, 1, amb_list, amb_count, nullptr, nullptr,
-                                                                   dlist + q0, 1);
-        RET(post_launch("k_argmin_exact_list", launches));
+        k_rowmin_exact_list<<<2 * ix->sm_count, MMIDX_NT, 0, st>>>(A32, xq, ix->dC.as<double>(), nlist, d, amb_list, amb_thr, amb_count, dlist + q0);
+        RET(post_launch("k_rowmin_exact_list", launches));
     }
     return MMIDX_OK;
 }

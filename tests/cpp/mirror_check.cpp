@@ -62,6 +62,31 @@ int main(int argc, char **argv) {
         EXPECT(ans.getDistances()[0] == (1 - 0.9) * (1 - 0.9));
         EXPECT(lin.computeNearestNeighbors(1, std::string("c")).getIds()[0] == "c");
         EXPECT(message_of([&] { lin.computeNearestNeighbors(1, std::vector<double>{1, 2}); }) == "The dimensionality of the vector is wrong!");
+        {  // RandomRotation with a supplied matrix == no transformation on the rotated vectors (RandomRotation.java:44-49)
+            const std::vector<double> pqcb = {0, 0, 4, 4, 0, 0, 4, 4};  // [m=2][ks=2][2]
+            const std::vector<double> R = {0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, -1, 0, 1, 0, 0};  // signed permutation, v R
+            auto rot = [&](const std::vector<double> &v) {
+                std::vector<double> o(4, 0.0);
+                for (int j = 0; j < 4; ++j)
+                    for (int i = 0; i < 4; ++i) o[j] += v[i] * R[i * 4 + j];
+                return o;
+            };
+            PQ a(4, 10, 2, 2, TransformationType::RandomRotation), b(4, 10, 2, 2);
+            a.loadProductQuantizer(pqcb);
+            b.loadProductQuantizer(pqcb);
+            EXPECT(a.rotationPending());
+            EXPECT(!message_of([&] { a.indexVector("x", {1, 2, 3, 4}); }).empty());  // no matrix yet: loud, not silently unrotated
+            EXPECT(message_of([&] { a.setRotation({1, 0, 0, 1}); }) == "the rotation matrix must be d x d");
+            a.setRotation(R);
+            const std::vector<std::vector<double>> X = {{1, 2, 3, 4}, {4, 4, 0, 0}, {0, -4, 5, 1}, {3, 3, 3, -3}};
+            for (size_t i = 0; i < X.size(); ++i) {
+                EXPECT(a.indexVector("v" + std::to_string(i), X[i]));
+                EXPECT(b.indexVector("v" + std::to_string(i), rot(X[i])));
+            }
+            const std::vector<double> q = {2, -3, 4, 1};
+            Answer ra = a.computeNearestNeighbors(4, q), rb = b.computeNearestNeighbors(4, rot(q));
+            EXPECT(ra.getIds() == rb.getIds() && ra.getDistances() == rb.getDistances() && ra.getIds().size() == 4);
+        }
         const std::vector<double> cb = {0, 0, 10, 10};
         VladAggregator agg(cb, 2, 2);
         const std::vector<double> v = agg.aggregate({{1, 1}, {9, 9}, {2, 0}});
