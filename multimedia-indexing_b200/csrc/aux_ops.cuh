@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_pca_project(const double *__restri
 __global__ void __launch_bounds__(MMIDX_NT) k_rotate_vectors(const double *__restrict__ X, const double *__restrict__ C,
                                                              const int32_t *__restrict__ list, int w,
                                                              const double *__restrict__ R, int d, double *__restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double *v = reinterpret_cast<double *>(smem_raw);  // [d]
     const int64_t g = blockIdx.x;
     const double *x = X + (g / w) * (int64_t)d;

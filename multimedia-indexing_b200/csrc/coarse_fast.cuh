@@ -147,7 +147,7 @@ constexpr size_t TM_SMEM = (size_t)2 * (TM_BM + TM_BN) * TM_LD * sizeof(unsigned
 __global__ void __launch_bounds__(MMIDX_NT) k_coarse_mma(const double *__restrict__ Q, const unsigned short *__restrict__ Ch,
                                                          const unsigned short *__restrict__ Cl, const float *__restrict__ c2,
                                                          int64_t nq, int nlist, int d, int dpad, float *__restrict__ A32) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned short *Ah = reinterpret_cast<unsigned short *>(smem_raw);  // [TM_BM][TM_LD]
     unsigned short *Al = Ah + TM_BM * TM_LD;
     unsigned short *Bh = Al + TM_BM * TM_LD;                            // [TM_BN][TM_LD]

@@ -174,7 +174,7 @@ struct TieMultiArgs {
 // per candidate -- ~50 us per flagged query instead of re-deriving every candidate from the quantizers.  use_lut == 0
 // (table larger than the shared memory the host granted): table-free evaluation.
 __global__ void __launch_bounds__(MMIDX_NT) k_tie_collect_multi(TieMultiArgs a, int use_lut) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int warp_sums[MMIDX_NT / 32];
     const TieDirectArgs &r = a.t;
     double *rv = reinterpret_cast<double *>(smem_raw);  // [d]   transformed residual of the current probe

@@ -97,7 +97,7 @@ constexpr int RCH = 4096;
 template <int M>
 __global__ void __launch_bounds__(MMIDX_NT) k_reorder_lists(const uint8_t *__restrict__ codes, const int64_t *__restrict__ list_off,
                                                             const int32_t *__restrict__ list_len, int32_t *__restrict__ src) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t(*cs)[M] = reinterpret_cast<uint8_t(*)[M]>(smem_raw);  // [RCH][M]
     __shared__ int load[M][32];
     __shared__ int mx[M];
@@ -280,6 +280,7 @@ struct FastArgs {
     int d, m, ks, S, w, k, nsplit;
     int flat;                   // flat PQ index: every (pseudo) list shares coarse row 0 (a zero centroid)
     int resolve_ties;           // 1: replay the queue's tie rule inside the kernel (unsharded, nsplit == 1)
+    int desc_stage;             // 1: the launch carries w * fast_desc_stride(m) extra bytes of shared memory for the descriptors
     int32_t *fb_list;           // (q*nsplit + s) items whose error band overflowed the collector
     int32_t *fb_count;
     unsigned long long *stats;  // optional [4]: candidates, re-scanned lists, exact evaluations, direct fallbacks
@@ -818,6 +819,9 @@ __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t
 // instantiation is the kernel exactly as tuned for them.  (Also measured and rejected for the HBM-streaming regime: four
 // 128-bit loads in flight per thread at 3 CTAs/SM -- slower at every batch size.)
 constexpr int FAST_SEG = 8192;
+#ifndef MMIDX_SCAN_STAGE
+#define MMIDX_SCAN_STAGE 1  // A/B switch (profiles/run_r2_ab2.sh): probe descriptors staged in shared memory
+#endif
 
 template <int CAP32, int M, bool LONG>
 __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
@@ -847,27 +851,36 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
     const int tid = threadIdx.x;
     const int s = blockIdx.x;
     const int64_t q = a.qorder ? (int64_t)a.qorder[blockIdx.y] : (int64_t)blockIdx.y;
-    const unsigned char *dq = a.desc + q * (int64_t)a.w * DSTRIDE;
+    const unsigned char *dqg = a.desc + q * (int64_t)a.w * DSTRIDE;
     const uint32_t t1_bytes = (uint32_t)(nent * sizeof(float));
     const int S = a.S;
     constexpr double rel = (double)M * 5.9604644775390625e-08;
     const float finf = __int_as_float(0x7f800000);
 
+    const double bq_q = a.bq[q];
+    const bool out_of_range = !(bq_q == bq_q);  // k_fast_prep: the query is outside the fp32-safe window
+    const int nop = out_of_range ? 0 : a.ocnt[q];
     c32.init();
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_fence_init();
+        if (s < nop) {
+            const int l0 = reinterpret_cast<const ProbeHdr *>(dqg + (int64_t)s * DSTRIDE)->l;
+            mbar_arrive_expect_tx(&bars[0], t1_bytes);
+            tma_load_1d(lut0, a.T1 + (int64_t)l0 * nent, t1_bytes, &bars[0]);
+        }
     }
     for (int i = tid; i < a.d; i += MMIDX_NT) qv[i] = a.Q[q * (int64_t)a.d + i];
-    __syncthreads();
-    const double bq_q = a.bq[q];
-    const bool out_of_range = !(bq_q == bq_q);  // k_fast_prep: the query is outside the fp32-safe window
-    const int nop = out_of_range ? 0 : a.ocnt[q];
-    if (tid == 0 && s < nop) {
-        const int l0 = reinterpret_cast<const ProbeHdr *>(dq + (int64_t)s * DSTRIDE)->l;
-        mbar_arrive_expect_tx(&bars[0], t1_bytes);
-        tma_load_1d(lut0, a.T1 + (int64_t)l0 * nent, t1_bytes, &bars[0]);
+    // The query's probe descriptors, staged once: a probe then starts with a shared-memory read instead of a dependent
+    // L2 round trip (the host grants the room only where it does not cost a resident CTA).
+    const unsigned char *dq = dqg;
+    if (a.desc_stage) {
+        uint4 *dsm = reinterpret_cast<uint4 *>(bars + 2);
+        const uint4 *src = reinterpret_cast<const uint4 *>(dqg);
+        for (int i = tid; i < nop * (DSTRIDE / 16); i += MMIDX_NT) dsm[i] = src[i];
+        dq = reinterpret_cast<const unsigned char *>(dsm);
     }
+    __syncthreads();
     // ---- per-query prologue: this query's T2 row (k_fast_t2) into shared memory.  Thread tid owns the float4
     //      entries tid + 256*r of every table (t2, stage, lut): it only ever re-reads what it wrote itself. ----
     float4 *t2v = reinterpret_cast<float4 *>(t2);
@@ -962,22 +975,32 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
                 // One 128-bit load per thread and step; the load of the next step is issued before the current one is
                 // consumed.  (Measured alternatives, profiles/README.md: L1 prefetch one or two steps ahead, two or four
                 // loads per step, 3 CTAs/SM with 80 registers -- all slower than this form.)
+                // Two steps per trip with the roles of the two code registers swapped, so that nothing is moved between
+                // them (SASS: 72 -> 60 instructions per step); a lane past the end of the list keeps a stale word -- every
+                // byte is a valid table index and the (i < len) predicate gates the offer.
                 constexpr int CPT = (M == 8) ? 2 : 1;
                 constexpr int STEP = MMIDX_NT * CPT;
                 int i0 = tid * CPT;
-                uint4 cur = make_uint4(0, 0, 0, 0);
-                if (i0 < len) cur = ld_nc_u4(lc + (int64_t)i0 * M);
-                for (int wb = (tid & ~31) * CPT; wb < len; wb += STEP) {  // warp-uniform trip count
-                    const int i1 = i0 + STEP;
-                    uint4 nxt = make_uint4(0, 0, 0, 0);
-                    if (i1 < len) nxt = ld_vol_u4(lc + (int64_t)i1 * M);
+                const uint8_t *pc = lc + (int64_t)i0 * M;
+                // (requesting the list's first word before the table build, so that its latency overlaps the build and the
+                //  barrier, was measured: 1.5 % slower -- four more live registers across the settle)
+                uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+                if (i0 < len) cur = ld_nc_u4(pc);
+                auto offer = [&](const uint4 cw, const int i) {
                     float d0, d1;
-                    adc_pair<M>(lut_s, cur, d0, d1);
-                    const bool p0 = (i0 < len) && d0 <= thr32;
-                    const bool p1 = (M == 8) && (i0 + 1 < len) && d1 <= thr32;
-                    if (__any_sync(0xffffffffu, p0 | p1)) c32.push2(p0, d0, p1, d1, ptag | (unsigned int)i0);
-                    cur = nxt;
-                    i0 = i1;
+                    adc_pair<M>(lut_s, cw, d0, d1);
+                    const bool p0 = (i < len) && d0 <= thr32;
+                    const bool p1 = (M == 8) && (i + 1 < len) && d1 <= thr32;
+                    if (__any_sync(0xffffffffu, p0 | p1)) c32.push2(p0, d0, p1, d1, ptag | (unsigned int)i);
+                };
+                for (int wb = (tid & ~31) * CPT; wb < len; wb += 2 * STEP) {  // warp-uniform trip count
+                    if (i0 + STEP < len) nxt = ld_vol_u4(pc + (int64_t)STEP * M);
+                    offer(cur, i0);
+                    if (wb + STEP >= len) break;  // warp-uniform
+                    if (i0 + 2 * STEP < len) cur = ld_vol_u4(pc + (int64_t)2 * STEP * M);
+                    offer(nxt, i0 + STEP);
+                    i0 += 2 * STEP;
+                    pc += (int64_t)2 * STEP * M;
                 }
             }
         }

@@ -251,6 +251,7 @@ struct mmidx_index {
     bool force_exact = false;  // MMIDX_MODE=exact
     bool want_stats = false;   // MMIDX_STATS=1
     size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
+    size_t smem_per_sm = 228 * 1024;  // shared memory of one SM (cudaDevAttrMaxSharedMemoryPerMultiprocessor)
     int sm_count = 148;        // SMs of this device: grids are sized in CTA slots = sm_count x resident CTAs per SM
     uint64_t gen = 0;          // bumped by everything that invalidates captured search graphs
     bool use_graph = true;     // MMIDX_GRAPH=0: always enqueue kernel by kernel
@@ -268,6 +269,7 @@ static inline int cta_slots(const mmidx_index *ix) { return ix->sm_count * 4; }
 
 static bool fast_eligible(const mmidx_index *ix);
 static void drop_graphs(mmidx_index *ix);
+static void free_graph_caches(mmidx_index *ix);  // GraphCache is complete only further down
 static void comm_release(mmidx_index *ix);
 
 static int check_device(int device) {
@@ -371,7 +373,10 @@ extern "C" int mmidx_create(const mmidx_params *pp, mmidx_t **out) {
     }
     {
         cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) ix->sm_count = prop.multiProcessorCount;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) {
+            ix->sm_count = prop.multiProcessorCount;
+            if (prop.sharedMemPerMultiprocessor > 0) ix->smem_per_sm = prop.sharedMemPerMultiprocessor;
+        }
     }
     if (const char *e = getenv("MMIDX_GRAPH")) ix->use_graph = atoi(e) != 0;
     if (const char *e = getenv("MMIDX_MODE")) ix->force_exact = strcmp(e, "exact") == 0;
@@ -411,9 +416,7 @@ extern "C" int mmidx_destroy(mmidx_t *ix) {
             fprintf(stderr, "[mmidx stats] candidates=%llu rescanned_lists=%llu survivors=%llu direct_fallbacks=%llu\n", h[0], h[1], h[2], h[3]);
         }
         cudaDeviceSynchronize();
-        drop_graphs(ix);
-        for (auto &kv : ix->graphs) delete kv.second;
-        ix->graphs.clear();
+        free_graph_caches(ix);
         for (auto &kv : ix->thread_streams) cudaStreamDestroy(kv.second);
         for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
         comm_release(ix);
@@ -1735,7 +1738,15 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
     RET(sc.get(&a.fb_list, (size_t)nq * nsplit));
     RET(sc.get(&a.fb_count, 1));
     CK(cudaMemsetAsync(a.fb_count, 0, sizeof(int32_t), st));
-    const size_t smem = fast_smem_bytes<CAP32, M>(ix->p.ks, ix->S, ix->p.d);
+    size_t smem = fast_smem_bytes<CAP32, M>(ix->p.ks, ix->S, ix->p.d);
+    {
+        // room for the query's descriptors in shared memory, if it does not cost a resident CTA (4 per SM by registers)
+        const size_t per_sm = ix->smem_per_sm, blk = 1024;  // 1 KB per CTA is reserved by the driver
+        const size_t ctas = std::min<size_t>(4, per_sm / (smem + blk));
+        const size_t desc_bytes = (size_t)w * fast_desc_stride(M);
+        a.desc_stage = (MMIDX_SCAN_STAGE && ctas > 0 && smem + desc_bytes + blk <= per_sm / ctas) ? 1 : 0;
+        if (a.desc_stage) smem += desc_bytes;
+    }
     // lists longer than FAST_SEG entries (pseudo lists of a large flat PQ index) take the segmented sweep
     auto scan_kernel = ix->long_lists ? k_ivfpq_scan_fast<CAP32, M, true> : k_ivfpq_scan_fast<CAP32, M, false>;
     RET(set_smem(scan_kernel, smem));
@@ -1991,6 +2002,13 @@ static void drop_graphs(mmidx_index *ix) {
         std::lock_guard<std::mutex> lk2(kv.second->mu);
         clear_cache(*kv.second);
     }
+}
+
+static void free_graph_caches(mmidx_index *ix) {
+    drop_graphs(ix);
+    std::lock_guard<std::mutex> lk(ix->graph_mu);
+    for (auto &kv : ix->graphs) delete kv.second;
+    ix->graphs.clear();
 }
 
 // The stream a host-pointer search call of this thread runs on.  One stream per calling thread: concurrent
