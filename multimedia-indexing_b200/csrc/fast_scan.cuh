@@ -35,6 +35,21 @@
 #include "tie_resolve.cuh"
 #include "topk.cuh"
 
+// ---- build-time switches of the fused scan kernel (defaults = the measured best; profiles/run_r2_ab2.sh builds variants) ----
+#ifndef MMIDX_SCAN_LB16
+#define MMIDX_SCAN_LB16 3  // resident CTAs per SM the m = 16 kernel is compiled for: shared memory allows 3, so 80
+                           // registers instead of 64 (config 4 scan 4.29 -> 4.01 ms, profiles/README.md)
+#endif
+#ifndef MMIDX_SCAN_HOIST16
+#define MMIDX_SCAN_HOIST16 1  // m = 16 (80 registers): the list's first code word is requested before the table build (-2 %)
+#endif
+#ifndef MMIDX_SELECT_PASSES
+#define MMIDX_SELECT_PASSES 3  // radix passes of the collector's threshold selection (4: the exact k-th key)
+#endif
+#ifndef MMIDX_SCAN_STAGE
+#define MMIDX_SCAN_STAGE 1  // A/B switch (profiles/run_r2_ab2.sh): probe descriptors staged in shared memory
+#endif
+
 namespace mmidx {
 
 // ---- index-time tables ------------------------------------------------------------------------------
@@ -317,7 +332,7 @@ struct TopK32 {
     static constexpr int PER = CAP / MMIDX_NT;
     float key[CAP];
     unsigned int pk[CAP];  // (probe rank << 22) | position inside the (re-ordered) list
-    unsigned int hist[256];
+    unsigned int hist[2][256];
     float thr32;  // admission threshold: candidates with d32 > thr32 are provably outside the result
     int cnt, overflow;
     int ovf;  // a barrier-free list scan ran out of slots: its entries are dropped and the list is scanned again
@@ -413,15 +428,22 @@ struct TopK32 {
         }
     }
 
-    // k-th smallest key (1-based) among the first n entries, n >= k >= 1; 4 radix passes of 8 bits
+    // An upper bound of the k-th smallest key (1-based) among the first n entries, n >= k >= 1, that is at most 2^-15
+    // (relative) above it: MMIDX_SELECT_PASSES = 3 radix passes of 8 bits locate the key's 24-bit prefix and the largest value
+    // with that prefix is returned (any bound >= the k-th key keeps the survivor set complete; a looser one only keeps a
+    // few more).  A non-finite bound (prefix of inf / nan patterns) takes the fourth pass: the exact key.
+    // Two histograms alternate, so that zeroing the next one needs no barrier of its own.
     __device__ float select_kth(int n, int k) {
         const int tid = threadIdx.x;
         unsigned prefix = 0, krem = (unsigned)k;
+        hist[0][tid] = 0;
+        __syncthreads();
+        int pass = 0;
 #pragma unroll 1
-        for (int pass = 0; pass < 4; ++pass) {
+        for (; pass < 4; ++pass) {
             const int shift = 24 - 8 * pass;
-            hist[tid] = 0;
-            __syncthreads();
+            unsigned int *h = hist[pass & 1];
+            hist[(pass + 1) & 1][tid] = 0;  // last read two barriers ago
             for (int i0 = 0; i0 < n; i0 += MMIDX_NT) {
                 const int i = i0 + tid;
                 bool act = i < n;
@@ -431,14 +453,14 @@ struct TopK32 {
                     act = (pass == 0 || (kk >> (shift + 8)) == prefix);
                     bin = (kk >> shift) & 255u;
                 }
-                hist_add(hist, act, bin);
+                hist_add(h, act, bin);
             }
             __syncthreads();
             if (tid < 32) {
                 unsigned loc[8], sum = 0;
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    loc[b] = hist[tid * 8 + b];
+                    loc[b] = h[tid * 8 + b];
                     sum += loc[b];
                 }
                 unsigned incl = sum;
@@ -467,8 +489,11 @@ struct TopK32 {
             __syncthreads();
             prefix = (prefix << 8) | (unsigned)s_bin;
             krem = (unsigned)s_krem;
+            if (pass == MMIDX_SELECT_PASSES - 1 && pass < 3) {
+                const float edge = f32_unkey((prefix << (shift)) | ((1u << shift) - 1u));
+                if (edge <= 3.4028234663852886e38f) return edge;  // block-uniform
+            }
         }
-        __syncthreads();
         return f32_unkey(prefix);
     }
 
@@ -819,12 +844,9 @@ __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t
 // instantiation is the kernel exactly as tuned for them.  (Also measured and rejected for the HBM-streaming regime: four
 // 128-bit loads in flight per thread at 3 CTAs/SM -- slower at every batch size.)
 constexpr int FAST_SEG = 8192;
-#ifndef MMIDX_SCAN_STAGE
-#define MMIDX_SCAN_STAGE 1  // A/B switch (profiles/run_r2_ab2.sh): probe descriptors staged in shared memory
-#endif
 
 template <int CAP32, int M, bool LONG>
-__global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
+__global__ void __launch_bounds__(MMIDX_NT, (M == 16 && MMIDX_SCAN_LB16 == 3) ? 3 : 4) k_ivfpq_scan_fast(FastArgs a, TopkOut o) {
     constexpr int ECAP = FastExactCap<CAP32, M>::value;
     constexpr int ks = 256;  // the fused kernel is specialised for full byte codes (host checks ks == 256)
     constexpr int nent = M * ks;
@@ -932,6 +954,8 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
         const int64_t start = (int64_t)(((unsigned long long)(unsigned int)hd.y << 32) | (unsigned long long)(unsigned int)hd.x);
         const int len = hd.z;  // > 0 by construction of the descriptors
         const uint8_t *lc = a.ocodes + start * M;
+        uint4 first = make_uint4(0, 0, 0, 0);
+        if (MMIDX_SCAN_HOIST16 && M == 16 && tid < len) first = ld_nc_u4(lc + (int64_t)tid * M);
         mbar_wait(&bars[0], (uint32_t)(it & 1));
         // ADC table of this probe: lut = (T1[l] + T2) + s
         {
@@ -984,8 +1008,8 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
                 const uint8_t *pc = lc + (int64_t)i0 * M;
                 // (requesting the list's first word before the table build, so that its latency overlaps the build and the
                 //  barrier, was measured: 1.5 % slower -- four more live registers across the settle)
-                uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-                if (i0 < len) cur = ld_nc_u4(pc);
+                uint4 cur = first, nxt = make_uint4(0, 0, 0, 0);
+                if (!(MMIDX_SCAN_HOIST16 && M == 16 && seg0 == 0) && i0 < len) cur = ld_nc_u4(pc);
                 auto offer = [&](const uint4 cw, const int i) {
                     float d0, d1;
                     adc_pair<M>(lut_s, cw, d0, d1);
@@ -1060,6 +1084,7 @@ __global__ void __launch_bounds__(MMIDX_NT, 4) k_ivfpq_scan_fast(FastArgs a, Top
                 const double qs = qv[src];
                 const double *Cs = a.C + src;
                 const double *Pj = a.P + (int64_t)j * ks * S + t;
+                // (unrolling this loop four times for more loads in flight was measured: 1 % slower)
                 for (int e = e0; e < nb; e += epb) {
                     const unsigned int code = scode[(b0 + e) * M + j];
                     const double r = __dsub_rn(Cs[(int64_t)s_l[b0 + e] * d], qs);  // residual = centroid - query

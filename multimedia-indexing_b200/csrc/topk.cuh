@@ -13,6 +13,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef MMIDX_RANK_SORT
+#define MMIDX_RANK_SORT 1  // A/B switch (profiles/run_r2_ab2.sh)
+#endif
+
 namespace mmidx {
 
 // histogram increment with warp aggregation: lanes that hit the same bin issue ONE shared-memory atomic
@@ -237,6 +241,36 @@ struct TopK {
     // distances the later-offered (larger seq) first.  Entries [n, next power of two) are overwritten with padding.
     __device__ void sort_first(int n) {
         const int tid = threadIdx.x;
+#if MMIDX_RANK_SORT
+        if (n <= MMIDX_NT) {
+            // One element per thread: its position is the number of entries that precede it in the queue's order
+            // (distance ascending, then the later offer first; the offer sequence is unique, so positions are too).
+            // n broadcast reads per thread and two barriers instead of log^2 n / 2 exchange stages with a barrier each.
+            __syncthreads();
+            double dv = 0.0;
+            unsigned long long sv = 0ull;
+            int pv = 0, rank = 0;
+            if (tid < n) {
+                dv = dist[tid];
+                sv = seq[tid];
+                pv = pay[tid];
+#pragma unroll 4
+                for (int i = 0; i < n; ++i) {
+                    const double di = dist[i];
+                    const unsigned long long si = seq[i];
+                    rank += (di < dv || (di == dv && si > sv)) ? 1 : 0;
+                }
+            }
+            __syncthreads();
+            if (tid < n) {
+                dist[rank] = dv;
+                seq[rank] = sv;
+                pay[rank] = pv;
+            }
+            __syncthreads();
+            return;
+        }
+#endif
         int n2 = 1;
         while (n2 < n) n2 <<= 1;
         __syncthreads();
