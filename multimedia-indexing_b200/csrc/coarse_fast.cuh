@@ -139,19 +139,31 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// CTA tile 128 queries x 64 centroids, 8 warps as 4 x 2, warp tile 32 x 32 (2 x 4 HMMA tiles), K chunk 64.
-// Shared rows are padded to 72 bf16 (36 words): the 8 rows a fragment load touches fall into distinct banks.
-constexpr int TM_BM = 128, TM_BN = 64, TM_BK = 64, TM_LD = TM_BK + 8;
-constexpr size_t TM_SMEM = (size_t)2 * (TM_BM + TM_BN) * TM_LD * sizeof(unsigned short);
+// CTA tile 128 queries x 64 centroids, 8 warps as 4 x 2, warp tile 32 x 32 (2 x 4 HMMA tiles), K chunks of 64 in two
+// shared-memory stages filled with cp.async (the next chunk lands while the current one is multiplied); fragments come
+// from ldmatrix.x4.  Both operands arrive pre-split (k_coarse_split_tables: the queries once per batch instead of once per
+// column of CTAs -- at nlist = 8192 that was 128 conversions of every query from binary64).
+// Shared rows are padded to 72 bf16 (144 bytes): the 8 rows of an ldmatrix phase fall into distinct bank groups.
+constexpr int TM_BM = 128, TM_BN = 64, TM_BK = 64, TM_LD = TM_BK + 8, TM_STAGES = 2;
+constexpr size_t TM_STAGE_ELEMS = (size_t)2 * (TM_BM + TM_BN) * TM_LD;
+constexpr size_t TM_SMEM = TM_STAGES * TM_STAGE_ELEMS * sizeof(unsigned short);
 
-__global__ void __launch_bounds__(MMIDX_NT) k_coarse_mma(const double *__restrict__ Q, const unsigned short *__restrict__ Ch,
-                                                         const unsigned short *__restrict__ Cl, const float *__restrict__ c2,
-                                                         int64_t nq, int nlist, int d, int dpad, float *__restrict__ A32) {
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem, bool valid) {
+    const int sz = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *smem) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem)));
+}
+
+__global__ void __launch_bounds__(MMIDX_NT) k_coarse_mma(const unsigned short *__restrict__ Qh, const unsigned short *__restrict__ Ql,
+                                                         const unsigned short *__restrict__ Ch, const unsigned short *__restrict__ Cl,
+                                                         const float *__restrict__ c2, int64_t nq, int nlist, int dpad,
+                                                         float *__restrict__ A32) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned short *Ah = reinterpret_cast<unsigned short *>(smem_raw);  // [TM_BM][TM_LD]
-    unsigned short *Al = Ah + TM_BM * TM_LD;
-    unsigned short *Bh = Al + TM_BM * TM_LD;                            // [TM_BN][TM_LD]
-    unsigned short *Bl = Bh + TM_BN * TM_LD;
+    unsigned short *sm = reinterpret_cast<unsigned short *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;  // warp tile origin: rows wm*32, columns wn*32
     const int g = lane >> 2, tig = lane & 3;
@@ -164,56 +176,56 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_mma(const double *__restric
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) main_[i][j][r] = corr[i][j][r] = 0.f;
-    for (int k0 = 0; k0 < dpad; k0 += TM_BK) {
-        __syncthreads();
-        // queries: binary64 -> fp32 -> bf16 hi / lo
-        for (int e = tid; e < TM_BM * TM_BK; e += MMIDX_NT) {
-            const int r = e / TM_BK, kk = e - r * TM_BK;
-            const int64_t q = q0 + r;
-            const int col = k0 + kk;
-            float f = 0.f;
-            if (q < nq && col < d) f = __double2float_rn(Q[q * (int64_t)d + col]);
-            const __nv_bfloat16 h = __float2bfloat16_rn(f);
-            Ah[r * TM_LD + kk] = __bfloat16_as_ushort(h);
-            Al[r * TM_LD + kk] = __bfloat16_as_ushort(__float2bfloat16_rn(f - __bfloat162float(h)));
+    auto load_stage = [&](int stage, int k0) {
+        unsigned short *Ah = sm + stage * TM_STAGE_ELEMS, *Al = Ah + TM_BM * TM_LD;
+        unsigned short *Bh = Al + TM_BM * TM_LD, *Bl = Bh + TM_BN * TM_LD;
+        for (int e = tid; e < TM_BM * (TM_BK / 8); e += MMIDX_NT) {
+            const int r = e >> 3, k8 = (e & 7) * 8;
+            const bool valid = q0 + r < nq && k0 + k8 < dpad;
+            const int64_t off = valid ? (q0 + r) * (int64_t)dpad + k0 + k8 : 0;
+            cp_async_16(Ah + r * TM_LD + k8, Qh + off, valid);
+            cp_async_16(Al + r * TM_LD + k8, Ql + off, valid);
         }
-        // centroids: 128-bit copies of the split tables
         for (int e = tid; e < TM_BN * (TM_BK / 8); e += MMIDX_NT) {
-            const int r = e / (TM_BK / 8), k8 = (e - r * (TM_BK / 8)) * 8;
-            const int n = n0 + r;
-            uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
-            if (n < nlist && k0 + k8 < dpad) {
-                vh = *reinterpret_cast<const uint4 *>(Ch + (int64_t)n * dpad + k0 + k8);
-                vl = *reinterpret_cast<const uint4 *>(Cl + (int64_t)n * dpad + k0 + k8);
-            }
-            *reinterpret_cast<uint4 *>(Bh + r * TM_LD + k8) = vh;
-            *reinterpret_cast<uint4 *>(Bl + r * TM_LD + k8) = vl;
+            const int r = e >> 3, k8 = (e & 7) * 8;
+            const bool valid = n0 + r < nlist && k0 + k8 < dpad;
+            const int64_t off = valid ? (int64_t)(n0 + r) * dpad + k0 + k8 : 0;
+            cp_async_16(Bh + r * TM_LD + k8, Ch + off, valid);
+            cp_async_16(Bl + r * TM_LD + k8, Cl + off, valid);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    const int nk = (dpad + TM_BK - 1) / TM_BK;
+    load_stage(0, 0);
+    for (int kc = 0; kc < nk; ++kc) {
+        if (kc + 1 < nk) {
+            load_stage((kc + 1) & 1, (kc + 1) * TM_BK);
+            asm volatile("cp.async.wait_group 1;");  // everything but the chunk just requested has landed
+        } else {
+            asm volatile("cp.async.wait_group 0;");
         }
         __syncthreads();
+        const unsigned short *Ah = sm + (kc & 1) * TM_STAGE_ELEMS, *Al = Ah + TM_BM * TM_LD;
+        const unsigned short *Bh = Al + TM_BM * TM_LD, *Bl = Bh + TM_BN * TM_LD;
 #pragma unroll
         for (int ks = 0; ks < TM_BK; ks += 16) {
             uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int r = wm * 32 + i * 16 + g;
-                const int c = ks + 2 * tig;
-                ah[i][0] = *reinterpret_cast<const uint32_t *>(Ah + r * TM_LD + c);
-                ah[i][1] = *reinterpret_cast<const uint32_t *>(Ah + (r + 8) * TM_LD + c);
-                ah[i][2] = *reinterpret_cast<const uint32_t *>(Ah + r * TM_LD + c + 8);
-                ah[i][3] = *reinterpret_cast<const uint32_t *>(Ah + (r + 8) * TM_LD + c + 8);
-                al[i][0] = *reinterpret_cast<const uint32_t *>(Al + r * TM_LD + c);
-                al[i][1] = *reinterpret_cast<const uint32_t *>(Al + (r + 8) * TM_LD + c);
-                al[i][2] = *reinterpret_cast<const uint32_t *>(Al + r * TM_LD + c + 8);
-                al[i][3] = *reinterpret_cast<const uint32_t *>(Al + (r + 8) * TM_LD + c + 8);
+                // matrices: (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15) = a0..a3
+                const int off = (wm * 32 + i * 16 + (lane & 15)) * TM_LD + ks + 8 * (lane >> 4);
+                ldmatrix_x4(ah[i], Ah + off);
+                ldmatrix_x4(al[i], Al + off);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = wn * 32 + j * 8 + g;
-                const int c = ks + 2 * tig;
-                bh[j][0] = *reinterpret_cast<const uint32_t *>(Bh + n * TM_LD + c);
-                bh[j][1] = *reinterpret_cast<const uint32_t *>(Bh + n * TM_LD + c + 8);
-                bl[j][0] = *reinterpret_cast<const uint32_t *>(Bl + n * TM_LD + c);
-                bl[j][1] = *reinterpret_cast<const uint32_t *>(Bl + n * TM_LD + c + 8);
+            for (int jp = 0; jp < 2; ++jp) {
+                // matrices: (n 0-7, k 0-7), (n 0-7, k 8-15), (n 8-15, k 0-7), (n 8-15, k 8-15) = b[2jp][0..1], b[2jp+1][0..1]
+                const int off = (wn * 32 + jp * 16 + (lane & 7) + ((lane >> 4) << 3)) * TM_LD + ks + 8 * ((lane >> 3) & 1);
+                uint32_t r[4];
+                ldmatrix_x4(r, Bh + off);
+                bh[2 * jp][0] = r[0], bh[2 * jp][1] = r[1], bh[2 * jp + 1][0] = r[2], bh[2 * jp + 1][1] = r[3];
+                ldmatrix_x4(r, Bl + off);
+                bl[2 * jp][0] = r[0], bl[2 * jp][1] = r[1], bl[2 * jp + 1][0] = r[2], bl[2 * jp + 1][1] = r[3];
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -224,6 +236,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_mma(const double *__restric
                     mma_bf16_16816(corr[i][j], al[i], bh[j]);
                 }
         }
+        __syncthreads();  // the stage is refilled by the request of the next trip
     }
     // a = c2[c] - 2 (main + corr)
 #pragma unroll
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
     float *key = reinterpret_cast<float *>(qv + d);                 // [nlist]
     int *surv = reinterpret_cast<int *>(key + ((nlist + 1) & ~1));             // [CAP] centroid ids, later scratch of the tie rule
     double *xs = reinterpret_cast<double *>(surv + CAP);            // [vb][d + 1] squared terms of a batch of survivors
-    __shared__ unsigned int hist[256];
+    __shared__ unsigned int hist2[2][256];  // the passes alternate, so that zeroing the next one needs no barrier of its own
     __shared__ int s_bin, s_krem, s_ns;
     __shared__ double s_q2;
     const int tid = threadIdx.x;
@@ -292,6 +305,7 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
     for (int i = tid; i < d; i += MMIDX_NT) qv[i] = Q[q * (int64_t)d + i];
     for (int i = tid; i < nlist; i += MMIDX_NT) key[i] = arow[i];
     if (tid == 0) s_ns = 0;
+    hist2[0][tid] = 0;
     tk.init();  // barrier
     if (tid < 32) {
         double n2 = 0.0;
@@ -307,8 +321,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         const int shift = 24 - 8 * pass;
-        hist[tid] = 0;
-        __syncthreads();
+        unsigned int *hist = hist2[pass & 1];
+        hist2[(pass + 1) & 1][tid] = 0;
         for (int i0 = 0; i0 < nlist; i0 += MMIDX_NT) {
             const int i = i0 + tid;
             bool act = i < nlist;
@@ -391,9 +405,19 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
             for (int e = tid >> 5; e < nb; e += MMIDX_NT / 32) {  // warp <-> centroid row
                 const double *cr = C + (int64_t)surv[b0 + e] * d;
                 double *xr = xs + e * (d + 1);
-                for (int j = tid & 31; j < d; j += 32) {
-                    const double df = __dsub_rn(cr[j], qv[j]);
-                    xr[j] = __dmul_rn(df, df);
+                if ((d & 1) == 0) {  // two dimensions per lane and 128-bit load (rows are 16-byte aligned when d is even)
+                    for (int j = 2 * (tid & 31); j < d; j += 64) {
+                        const double2 cv = *reinterpret_cast<const double2 *>(cr + j);
+                        const double2 qq = *reinterpret_cast<const double2 *>(qv + j);
+                        const double d0 = __dsub_rn(cv.x, qq.x), d1 = __dsub_rn(cv.y, qq.y);
+                        xr[j] = __dmul_rn(d0, d0);
+                        xr[j + 1] = __dmul_rn(d1, d1);
+                    }
+                } else {
+                    for (int j = tid & 31; j < d; j += 32) {
+                        const double df = __dsub_rn(cr[j], qv[j]);
+                        xr[j] = __dmul_rn(df, df);
+                    }
                 }
             }
             __syncthreads();

@@ -336,6 +336,21 @@ static int post_launch(const char *name, int *launches) {
     return MMIDX_OK;
 }
 
+// Tensor-core coarse filter of n rows of X against the index's split centroid tables: A32[n][nlist].  The rows are split into
+// bf16 hi / lo once (Xh, Xl: [n][dpad] scratch of the caller), then k_coarse_mma runs on pre-split operands only.
+static int launch_coarse_mma(mmidx_index *ix, const double *X, int64_t n, float *A32, unsigned short *Xh, unsigned short *Xl,
+                             cudaStream_t st, int *launches) {
+    const int d = ix->p.d, nlist = ix->p.nlist, dpad = ix->dpad;
+    const size_t ne = (size_t)n * dpad;
+    k_coarse_split_tables<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, (int)n, d, dpad, Xh, Xl);
+    RET(post_launch("k_coarse_split_tables", launches));
+    RET(set_smem(k_coarse_mma, TM_SMEM));
+    dim3 gg((unsigned)((nlist + TM_BN - 1) / TM_BN), (unsigned)((n + TM_BM - 1) / TM_BM));
+    k_coarse_mma<<<gg, MMIDX_NT, TM_SMEM, st>>>(Xh, Xl, ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>(), ix->dc2.as<float>(), n,
+                                                nlist, dpad, A32);
+    return post_launch("k_coarse_mma", launches);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // lifecycle
 // ---------------------------------------------------------------------------------------------------------
@@ -518,11 +533,10 @@ extern "C" int mmidx_set_coarse_quantizer(mmidx_t *ix, const double *C) {
         RET(sc.get(&A32, (size_t)nsamp * nlist));
         RET(sc.get(&dmax, 1));
         CK(cudaMemsetAsync(dmax, 0, sizeof(double), ix->stream));
-        RET(set_smem(k_coarse_mma, TM_SMEM));
-        dim3 gg((unsigned)((nlist + TM_BN - 1) / TM_BN), (unsigned)((nsamp + TM_BM - 1) / TM_BM));
-        k_coarse_mma<<<gg, MMIDX_NT, TM_SMEM, ix->stream>>>(ix->dC.as<double>(), ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>(),
-                                                            ix->dc2.as<float>(), nsamp, nlist, d, dpad, A32);
-        RET(post_launch("k_coarse_mma", nullptr));
+        unsigned short *Xh, *Xl;
+        RET(sc.get(&Xh, (size_t)nsamp * dpad));
+        RET(sc.get(&Xl, (size_t)nsamp * dpad));
+        RET(launch_coarse_mma(ix, ix->dC.as<double>(), nsamp, A32, Xh, Xl, ix->stream, nullptr));
         k_coarse_filter_error<<<(unsigned)(((size_t)nsamp * nlist + 255) / 256), 256, 0, ix->stream>>>(
             ix->dC.as<double>(), ix->dC.as<double>(), A32, nsamp, nlist, d, (double)cm, dmax);
         RET(post_launch("k_coarse_filter_error", nullptr));
@@ -655,16 +669,17 @@ static int coarse_assign_dev(mmidx_index *ix, const double *dX, int64_t n, int32
     RET(sc.get(&amb_list, (size_t)cb));
     RET(sc.get(&amb_thr, (size_t)cb));
     RET(sc.get(&amb_count, 1));
+    unsigned short *Xh = nullptr, *Xl = nullptr;
+    if (ix->coarse_mma_ok) {
+        RET(sc.get(&Xh, (size_t)cb * ix->dpad));
+        RET(sc.get(&Xl, (size_t)cb * ix->dpad));
+    }
     for (int64_t q0 = 0; q0 < n; q0 += cb) {
         const int64_t nb = std::min(cb, n - q0);
         const double *xq = dX + q0 * d;
         double coef;
         if (ix->coarse_mma_ok) {
-            RET(set_smem(k_coarse_mma, TM_SMEM));
-            dim3 gg((unsigned)((nlist + TM_BN - 1) / TM_BN), (unsigned)((nb + TM_BM - 1) / TM_BM));
-            k_coarse_mma<<<gg, MMIDX_NT, TM_SMEM, st>>>(xq, ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>(), ix->dc2.as<float>(),
-                                                        nb, nlist, d, ix->dpad, A32);
-            RET(post_launch("k_coarse_mma", launches));
+            RET(launch_coarse_mma(ix, xq, nb, A32, Xh, Xl, st, launches));
             coef = coarse_coef_mma(d);
         } else {
             dim3 gg((unsigned)((nlist + CG_BN - 1) / CG_BN), (unsigned)((nb + CG_BM - 1) / CG_BM));
@@ -1126,11 +1141,10 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
         RET(sc.get(&A32, (size_t)nq * nlist));
         double coef;
         if (ix->coarse_mma_ok) {
-            RET(set_smem(k_coarse_mma, TM_SMEM));
-            dim3 gg((unsigned)((nlist + TM_BN - 1) / TM_BN), (unsigned)((nq + TM_BM - 1) / TM_BM));
-            k_coarse_mma<<<gg, MMIDX_NT, TM_SMEM, st>>>(dQ, ix->dCh.as<unsigned short>(), ix->dCl.as<unsigned short>(), ix->dc2.as<float>(),
-                                                        nq, nlist, d, ix->dpad, A32);
-            RET(post_launch("k_coarse_mma", launches));
+            unsigned short *Xh, *Xl;
+            RET(sc.get(&Xh, (size_t)nq * ix->dpad));
+            RET(sc.get(&Xl, (size_t)nq * ix->dpad));
+            RET(launch_coarse_mma(ix, dQ, nq, A32, Xh, Xl, st, launches));
             coef = coarse_coef_mma(d);
         } else {
             dim3 gg((unsigned)((nlist + CG_BN - 1) / CG_BN), (unsigned)((nq + CG_BM - 1) / CG_BM));
@@ -1705,7 +1719,7 @@ static int ivfpq_chunk_fast(mmidx_index *ix, const double *dQ, int64_t nq, int k
             RET(sc.get(&qorder, (size_t)nq));
         }
         StageMark sm(ix, st, 1);
-        const size_t psm = (size_t)a.d * 8 + (size_t)M * 8 + (size_t)w * 8 + 16;
+        const size_t psm = (size_t)(a.d + M) * 8 + (size_t)M * 8 + (size_t)w * 8 + 16;
         if (M == 8 && a.S == 16)
             k_fast_prep<8, 16><<<(unsigned)nq, MMIDX_NT, psm, st>>>(dQ, a.C, a.perm, dprobes, a.t1max, a.pmax, a.list_off, a.list_len, a.d, M, a.S, w, a.flat, desc, bq, oprobes, ocnt, work);
         else if (M == 16 && a.S == 8)
