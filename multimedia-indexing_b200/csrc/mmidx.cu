@@ -252,6 +252,7 @@ struct mmidx_index {
     bool want_stats = false;   // MMIDX_STATS=1
     size_t lut_chunk_bytes = (size_t)1024 << 20;  // ADC-table scratch per query chunk (MMIDX_LUT_CHUNK_MB)
     size_t smem_per_sm = 228 * 1024;  // shared memory of one SM (cudaDevAttrMaxSharedMemoryPerMultiprocessor)
+    int64_t host_chunk = 2560; // queries per pipelined chunk of mmidx_search (MMIDX_CHUNK; sweep in profiles/README.md)
     int sm_count = 148;        // SMs of this device: grids are sized in CTA slots = sm_count x resident CTAs per SM
     uint64_t gen = 0;          // bumped by everything that invalidates captured search graphs
     bool use_graph = true;     // MMIDX_GRAPH=0: always enqueue kernel by kernel
@@ -394,6 +395,7 @@ extern "C" int mmidx_create(const mmidx_params *pp, mmidx_t **out) {
         }
     }
     if (const char *e = getenv("MMIDX_GRAPH")) ix->use_graph = atoi(e) != 0;
+    if (const char *e = getenv("MMIDX_CHUNK")) ix->host_chunk = std::max(64, atoi(e));
     if (const char *e = getenv("MMIDX_MODE")) ix->force_exact = strcmp(e, "exact") == 0;
     if (const char *e = getenv("MMIDX_STATS")) ix->want_stats = atoi(e) != 0;
     if (const char *e = getenv("MMIDX_REORDER")) ix->reorder = atoi(e) != 0;
@@ -2312,7 +2314,7 @@ extern "C" int mmidx_search(mmidx_t *ix, int64_t nq, const double *Q, int32_t k,
     RET(sc.get(&dcnt, (size_t)nq));
     // Query chunks are pipelined over three streams: the host->device copy of chunk c+1 and the device->host copy of
     // chunk c-1 run under the kernels of chunk c (pinned host buffers; pageable ones still work, just serialised).
-    const int64_t CH = 2048;
+    const int64_t CH = ix->host_chunk;
     if (nq <= 2 * CH) {
         CK(cudaMemcpyAsync(dQ, Q, sizeof(double) * (size_t)nq * ix->p.d, cudaMemcpyHostToDevice, st));
         RET(prepare_search(ix, k));
