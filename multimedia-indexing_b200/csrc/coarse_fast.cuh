@@ -285,16 +285,19 @@ __global__ void k_coarse_filter_error(const double *__restrict__ Q, const double
 
 // grid nq.  Shared memory: TopK<CAP> | qv [d] | keys [nlist] fp32 | surv [CAP] | xs [vb][d + 1]
 
-template <int CAP>
-__global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__restrict__ Q, const double *__restrict__ C,
+// KPT > 0: nlist <= KPT * 256 and every thread keeps its KPT filter keys in registers (no key array in shared memory: at
+// nlist = 8192 that array was 32 KB per CTA and every pass re-read it); KPT == 0: keys staged in shared memory, any nlist.
+template <int CAP, int KPT>
+__global__ void __launch_bounds__(MMIDX_NT, KPT == 0 ? (CAP <= 256 ? 6 : 4) : (KPT <= 4 ? 6 : (KPT <= 16 ? 4 : 3))) k_coarse_verify(const double *__restrict__ Q, const double *__restrict__ C,
                                                             const float *__restrict__ A32, const float *__restrict__ cmax,
                                                             int nlist, int d, int w, int vb, double coef, TopkOut o) {
+    constexpr bool REGK = KPT > 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TopK<CAP> &tk = *reinterpret_cast<TopK<CAP> *>(smem_raw);
     const size_t tk_bytes = (sizeof(TopK<CAP>) + 127) & ~(size_t)127;
     double *qv = reinterpret_cast<double *>(smem_raw + tk_bytes);  // [d]
-    float *key = reinterpret_cast<float *>(qv + d);                 // [nlist]
-    int *surv = reinterpret_cast<int *>(key + ((nlist + 1) & ~1));             // [CAP] centroid ids, later scratch of the tie rule
+    float *key = reinterpret_cast<float *>(qv + d);                 // [nlist] (KPT == 0 only)
+    int *surv = reinterpret_cast<int *>(key + (REGK ? 0 : ((nlist + 1) & ~1)));  // [CAP] centroid ids, later scratch of the tie rule
     double *xs = reinterpret_cast<double *>(surv + CAP);            // [vb][d + 1] squared terms of a batch of survivors
     __shared__ unsigned int hist2[2][256];  // the passes alternate, so that zeroing the next one needs no barrier of its own
     __shared__ int s_bin, s_krem, s_ns;
@@ -303,7 +306,16 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
     const int64_t q = blockIdx.x;
     const float *arow = A32 + q * (int64_t)nlist;
     for (int i = tid; i < d; i += MMIDX_NT) qv[i] = Q[q * (int64_t)d + i];
-    for (int i = tid; i < nlist; i += MMIDX_NT) key[i] = arow[i];
+    float kreg[REGK ? KPT : 1];
+    if (REGK) {
+#pragma unroll
+        for (int r = 0; r < (REGK ? KPT : 1); ++r) {
+            const int i = tid + r * MMIDX_NT;
+            kreg[r] = i < nlist ? arow[i] : 0.f;
+        }
+    } else {
+        for (int i = tid; i < nlist; i += MMIDX_NT) key[i] = arow[i];
+    }
     if (tid == 0) s_ns = 0;
     hist2[0][tid] = 0;
     tk.init();  // barrier
@@ -323,17 +335,23 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
         const int shift = 24 - 8 * pass;
         unsigned int *hist = hist2[pass & 1];
         hist2[(pass + 1) & 1][tid] = 0;
-        for (int i0 = 0; i0 < nlist; i0 += MMIDX_NT) {
-            const int i = i0 + tid;
+        auto count_key = [&](int i, float kv) {
             bool act = i < nlist;
             unsigned bin = 0;
             if (act) {
-                unsigned u = __float_as_uint(key[i]);
+                unsigned u = __float_as_uint(kv);
                 u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
                 act = (pass == 0 || (u >> (shift + 8)) == prefix);
                 bin = (u >> shift) & 255u;
             }
             hist_add(hist, act, bin);
+        };
+        if (REGK) {
+#pragma unroll
+            for (int r = 0; r < (REGK ? KPT : 1); ++r)
+                if (r * MMIDX_NT < nlist) count_key(tid + r * MMIDX_NT, kreg[r]);  // block-uniform guard
+        } else {
+            for (int i0 = 0; i0 < nlist; i0 += MMIDX_NT) count_key(i0 + tid, (i0 + tid < nlist) ? key[i0 + tid] : 0.f);
         }
         __syncthreads();
         if (tid < 32) {
@@ -379,9 +397,8 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
     const double B = 1.02 * 5.9604644775390625e-08 * 2.0 * cm * cm + coef * qn * cm +
                      (d + 2.0) * 2.220446049250313e-16 * (qn + cm) * (qn + cm);
     const float lim = __double2float_ru((double)kth + 2.0 * B + 1e-30);
-    for (int i0 = 0; i0 < nlist; i0 += MMIDX_NT) {
-        const int i = i0 + tid;
-        const bool pred = i < nlist && key[i] <= lim;
+    auto keep_key = [&](int i, float kv) {
+        const bool pred = i < nlist && kv <= lim;
         const unsigned mask = __ballot_sync(0xffffffffu, pred);
         if (mask) {
             const int lane = tid & 31, leader = __ffs(mask) - 1;
@@ -391,6 +408,13 @@ __global__ void __launch_bounds__(MMIDX_NT) k_coarse_verify(const double *__rest
             const int slot = base + __popc(mask & ((1u << lane) - 1u));
             if (pred && slot < CAP) surv[slot] = i;
         }
+    };
+    if (REGK) {
+#pragma unroll
+        for (int r = 0; r < (REGK ? KPT : 1); ++r)
+            if (r * MMIDX_NT < nlist) keep_key(tid + r * MMIDX_NT, kreg[r]);
+    } else {
+        for (int i0 = 0; i0 < nlist; i0 += MMIDX_NT) keep_key(i0 + tid, (i0 + tid < nlist) ? key[i0 + tid] : 0.f);
     }
     __syncthreads();
     // outside the fp32-safe magnitude window (fast_scan.cuh) the filter proves nothing: rank by the exact sweep below

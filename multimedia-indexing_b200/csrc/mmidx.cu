@@ -267,6 +267,12 @@ struct mmidx_index {
 
 // CTA slots of the device for kernels that keep 4 CTAs per SM resident (the fused scan's launch bound)
 static inline int cta_slots(const mmidx_index *ix) { return ix->sm_count * 4; }
+#ifndef MMIDX_VERIFY_VB
+#define MMIDX_VERIFY_VB 16  // survivors whose squared terms are staged per batch of k_coarse_verify
+#endif
+#ifndef MMIDX_VERIFY_REGKEYS
+#define MMIDX_VERIFY_REGKEYS 1  // A/B switch: k_coarse_verify keeps its filter keys in registers when nlist <= 8192
+#endif
 
 static bool fast_eligible(const mmidx_index *ix);
 static void drop_graphs(mmidx_index *ix);
@@ -1128,8 +1134,10 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     const int ccap = w <= 128 ? 256 : cap_for(w);
     const size_t tkb = ccap == 256 ? topk_bytes<256>() : (ccap == 1024 ? topk_bytes<1024>() : topk_bytes<2048>());
     // survivors evaluated per batch: up to 16 rows of squared terms, at most 32 KB (at least one row)
-    const int vb = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)32 << 10) / ((size_t)(d + 1) * 8)));
-    const size_t vsm = tkb + (size_t)d * 8 + (((size_t)nlist * 4 + 7) & ~(size_t)7) + (size_t)ccap * 4 + (size_t)vb * (d + 1) * 8;
+    const int vb = (int)std::max<size_t>(1, std::min<size_t>(MMIDX_VERIFY_VB, ((size_t)2 * MMIDX_VERIFY_VB << 10) / ((size_t)(d + 1) * 8)));
+    // filter keys in registers (k_coarse_verify<256, KPT>): no key array in shared memory
+    const int kpt = (MMIDX_VERIFY_REGKEYS && ccap == 256 && nlist <= 32 * MMIDX_NT) ? (nlist <= 4 * MMIDX_NT ? 4 : (nlist <= 16 * MMIDX_NT ? 16 : 32)) : 0;
+    const size_t vsm = tkb + (size_t)d * 8 + (kpt ? 0 : (((size_t)nlist * 4 + 7) & ~(size_t)7)) + (size_t)ccap * 4 + (size_t)vb * (d + 1) * 8;
     const bool fastc = !ix->force_exact && ix->coarse_range_ok && vsm <= 160 * 1024;
     TieLists tl;
     RET(sc.get(&tl.seq, (size_t)nq * w));
@@ -1154,16 +1162,25 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
             RET(post_launch("k_coarse_f32", launches));
             coef = coarse_coef_ffma(d);
         }
-        if (ccap == 256) {
-            RET(set_smem(k_coarse_verify<256>, vsm));
-            k_coarse_verify<256><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, coef, o);
-        } else if (ccap == 1024) {
-            RET(set_smem(k_coarse_verify<1024>, vsm));
-            k_coarse_verify<1024><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, coef, o);
-        } else {
-            RET(set_smem(k_coarse_verify<2048>, vsm));
-            k_coarse_verify<2048><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, w, vb, coef, o);
-        }
+#define MMIDX_LAUNCH_VERIFY(CAPV, KPTV)                                                                                             \
+    do {                                                                                                                            \
+        RET(set_smem(k_coarse_verify<CAPV, KPTV>, vsm));                                                                            \
+        k_coarse_verify<CAPV, KPTV><<<(unsigned)nq, MMIDX_NT, vsm, st>>>(dQ, ix->dC.as<double>(), A32, ix->dcmax.as<float>(), nlist, d, \
+                                                                         w, vb, coef, o);                                           \
+    } while (0)
+        if (ccap == 256 && kpt == 4)
+            MMIDX_LAUNCH_VERIFY(256, 4);
+        else if (ccap == 256 && kpt == 16)
+            MMIDX_LAUNCH_VERIFY(256, 16);
+        else if (ccap == 256 && kpt == 32)
+            MMIDX_LAUNCH_VERIFY(256, 32);
+        else if (ccap == 256)
+            MMIDX_LAUNCH_VERIFY(256, 0);
+        else if (ccap == 1024)
+            MMIDX_LAUNCH_VERIFY(1024, 0);
+        else
+            MMIDX_LAUNCH_VERIFY(2048, 0);
+#undef MMIDX_LAUNCH_VERIFY
         RET(post_launch("k_coarse_verify", launches));
         // only rows ranked by the kernel's exact sweep (band wider than the collector) can be flagged here
         k_tie_collect_rows_direct<<<tg, MMIDX_NT, 0, st>>>(dQ, ix->dC.as<double>(), nlist, d, w, pd, amb_list, amb_count, tl);
