@@ -21,11 +21,14 @@ line reports beside it `list_sharded` (S = N: the north_star layout, per-shard q
 job batch) and `strong_scaling_10k` (10 000 queries in total, split over the ranks).
 
 Timing protocol: W >= 6 warm-up steps (the third call with a given shape is captured into a CUDA graph, once per window
-parity); every timed step is preceded by an L2 flush (256 MiB write, untimed) and, for N > 1, a barrier; K steps are timed
+parity); every timed step is preceded by an L2 flush (256 MiB write, untimed) and, for N > 1, a barrier followed by a
+common start instant on the node's monotonic clock (`Ctx.aligned_start`: the ranks leave a barrier with a skew of host
+wake-up latencies, which would otherwise be measured as waiting for peers' rows inside the step); K steps are timed
 per round and rounds repeat until the timed region holds >= 0.5 s; per step the MAX over ranks is taken; mean and median
 over all timed steps are reported (`value` uses the mean)."""
 import argparse
 import ctypes as C
+import gc
 import importlib.util
 import json
 import os
@@ -269,6 +272,19 @@ class Ctx:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def aligned_start(self, lead_s=250e-6):
+        """N > 1, after the barrier: all ranks agree on one instant of the node's monotonic clock (the latest rank's
+        now + lead) and spin until then, so that the timed step starts together on every rank.  Without it the skew with
+        which the ranks leave the barrier (tens to hundreds of microseconds of host wake-up) is measured as time the
+        early ranks spend waiting for the late ranks' rows inside the step."""
+        if self.dist is None:
+            return
+        t = self.torch.tensor([time.perf_counter() + lead_s], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        t0 = float(t.item())
+        while time.perf_counter() < t0:
+            pass
+
     def max_over_ranks(self, values):
         t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
         if self.dist is not None:
@@ -283,11 +299,21 @@ class Ctx:
             step()
         torch.cuda.synchronize()
         out = []
+        gc.collect()
+        gc.disable()  # a collection between the start event and the launch would be timed on this rank and, through the max, on all
+        try:
+            return self._timed_rounds(step, steps, after, wall, min_s, max_rounds, out)
+        finally:
+            gc.enable()
+
+    def _timed_rounds(self, step, steps, after, wall, min_s, max_rounds, out):
+        torch = self.torch
         for _ in range(max_rounds):
             ts = []
             for _ in range(steps):
                 self.flush.fill_(1)  # evict L2 between timed steps (untimed)
                 self.barrier()
+                self.aligned_start()
                 if wall:
                     t0 = time.perf_counter()
                     step()

@@ -268,7 +268,7 @@ struct mmidx_index {
 // CTA slots of the device for kernels that keep 4 CTAs per SM resident (the fused scan's launch bound)
 static inline int cta_slots(const mmidx_index *ix) { return ix->sm_count * 4; }
 #ifndef MMIDX_VERIFY_VB
-#define MMIDX_VERIFY_VB 16  // survivors whose squared terms are staged per batch of k_coarse_verify
+#define MMIDX_VERIFY_VB 0  // survivors whose squared terms are staged per batch of k_coarse_verify (0: chosen from w)
 #endif
 #ifndef MMIDX_VERIFY_REGKEYS
 #define MMIDX_VERIFY_REGKEYS 1  // A/B switch: k_coarse_verify keeps its filter keys in registers when nlist <= 8192
@@ -1133,8 +1133,10 @@ static int coarse_probe_dev(mmidx_index *ix, const double *dQ, int64_t nq, int w
     // the CTA's shared memory low (8 CTAs/SM at w <= 128).  More survivors than ccap -> the kernel's exact sweep.
     const int ccap = w <= 128 ? 256 : cap_for(w);
     const size_t tkb = ccap == 256 ? topk_bytes<256>() : (ccap == 1024 ? topk_bytes<1024>() : topk_bytes<2048>());
-    // survivors evaluated per batch: up to 16 rows of squared terms, at most 32 KB (at least one row)
-    const int vb = (int)std::max<size_t>(1, std::min<size_t>(MMIDX_VERIFY_VB, ((size_t)2 * MMIDX_VERIFY_VB << 10) / ((size_t)(d + 1) * 8)));
+    // survivors evaluated per batch: up to 16 / 32 rows of squared terms, at most 32 / 64 KB (at least one row)
+    // (measured, profiles/README.md: 16 rows are best for w = 32, 32 rows for w = 64 -- about w / 2 survivors per batch)
+    const size_t vcap = MMIDX_VERIFY_VB ? (size_t)MMIDX_VERIFY_VB : (w > 32 ? 32 : 16);
+    const int vb = (int)std::max<size_t>(1, std::min<size_t>(vcap, (2 * vcap << 10) / ((size_t)(d + 1) * 8)));
     // filter keys in registers (k_coarse_verify<256, KPT>): no key array in shared memory
     const int kpt = (MMIDX_VERIFY_REGKEYS && ccap == 256 && nlist <= 32 * MMIDX_NT) ? (nlist <= 4 * MMIDX_NT ? 4 : (nlist <= 16 * MMIDX_NT ? 16 : 32)) : 0;
     const size_t vsm = tkb + (size_t)d * 8 + (kpt ? 0 : (((size_t)nlist * 4 + 7) & ~(size_t)7)) + (size_t)ccap * 4 + (size_t)vb * (d + 1) * 8;
