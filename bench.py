@@ -343,9 +343,11 @@ MULTI_STAGES = ("coarse", "prep", "scan", "after_scan", "whole_call", "exchange_
 
 def summarize(times_ms, queries_per_step):
     mean, med = float(np.mean(times_ms)), float(np.median(times_ms))
+    pct = {f"p{q}": float(np.percentile(times_ms, q)) for q in (10, 90, 99)}
+    pct["max"] = float(np.max(times_ms))
     return {"value": queries_per_step / (mean * 1e-3), "ms_per_step": mean, "median_ms_per_step": med,
             "value_at_median": queries_per_step / (med * 1e-3), "timed_steps": len(times_ms),
-            "timed_region_s": float(np.sum(times_ms)) * 1e-3}
+            "timed_region_s": float(np.sum(times_ms)) * 1e-3, "step_ms_percentiles": pct}
 
 
 def ptr(t):
@@ -818,6 +820,7 @@ def run_gpu(args, rank, world, local_rank):
                   "and stores its rows into all ranks' exchange windows (NVLink P2P, no collective call)",
         "l2": "flushed between timed steps (256 MiB write)",
         "median_ms_per_step": main["median_ms_per_step"], "value_at_median": main["value_at_median"],
+        "step_ms_percentiles": main.get("step_ms_percentiles"),
         "timed_steps": main["timed_steps"], "timed_region_s": main["timed_region_s"],
         "training": f"{wl['NTRAIN']} points, {wl['ITERS']} Lloyd iterations (SURVEY 8d)",
         "recall_at_100": rec,
@@ -1045,6 +1048,7 @@ def run_gpu_cfg4(args, ctx, M, synth, wl):
         "config": {"workload": wl["name"] if N_DB == wl["N_DB"] else wl["name"] + f" [reduced to {N_DB} vectors]", "nq_per_step": NQ, "k": K},
         "layout": f"{world} list shards x 1 group (per-shard queues stored into the slice owners' windows, device merge)" if world > 1 else "1 GPU",
         "median_ms_per_step": head["median_ms_per_step"], "timed_steps": head["timed_steps"], "timed_region_s": head["timed_region_s"],
+        "step_ms_percentiles": head.get("step_ms_percentiles"),
         "stage_ms_per_step": head["stage_ms_per_step"],
         "roofline": {"bound": "hbm", "kernel": "k_ivfpq_scan_fast<2048,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
