@@ -219,6 +219,14 @@ def test_coarse_probes_vs_oracle(mode, monkeypatch):
     ix = make_ivfpq(d, m, ks, 1600, 40, Cb, P)
     Qb = np.vstack([Cq[:1] + 0.5, Q[:7]])
     assert (ix.computeNearestCoarseIndices(Qb) == O.coarse_topw(Cb, Qb, 40)).all(), "wide tie class"
+    # (d) the register-key instantiations of the verification (16 and 32 keys per thread), ragged last block of keys,
+    #     duplicated centroids among them
+    for nl, w in ((2048, 64), (5000, 64), (8192, 33)):
+        Cl = rng.normal(60, 25, size=(nl, d))
+        Cl[nl // 2:nl // 2 + 40] = Cl[:40]
+        ix = make_ivfpq(d, m, ks, nl, w, Cl, P)
+        Ql = np.vstack([Cl[:3] + 0.25, Q[:13]])
+        assert (ix.computeNearestCoarseIndices(Ql) == O.coarse_topw(Cl, Ql, w)).all(), f"nlist={nl}"
 
 
 def test_bulk_reload_matches_incremental_index():
