@@ -202,3 +202,71 @@ def test_multi_step_on_one_gpu():
         assert (row0, nrows) == (0, nq)
         assert (iids[:nq].cpu().numpy() == oi).all() and (dd[:nq].cpu().numpy() == od).all() and (cnt[:nq].cpu().numpy() == oc).all(), step
     mi.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.timeout(600)
+def test_one_process_one_thread_per_gpu(monkeypatch):
+    """The embedding of a single JVM: ONE process, one host thread per GPU.  mmidx_comm_attach maps a same-process peer's window
+    by plain peer access instead of CUDA IPC; the two threads then step through mmidx_search_multi (host buffers) together.
+    Two list shards, result == the unsharded oracle."""
+    import ctypes as C
+    import threading
+
+    import mmidx_b200 as M
+    import pyoracle as O
+    from multimedia_indexing_b200 import _capi, synth
+    from multimedia_indexing_b200._capi import check, lib
+
+    monkeypatch.setenv("MMIDX_COMM_TIMEOUT_S", "30")
+    d, m, ks, nlist, w, k, n, nq, S = 32, 8, 256, 48, 12, 10, 12000, 333, 2
+    ce = synth.mixture_centers(d, 64)
+    X, Q = synth.mixture(n, d, 1, ce), synth.mixture(nq, d, 2, ce)
+    Cq, P = synth.train_ivfpq(d, m, ks, nlist, ntrain=4000, iters=3, centers=ce)
+    idx, handles = [], []
+    for r in range(S):
+        ix = M.IVFPQ(d, n, m, ks, M.TransformationType.None_, nlist, device=r, shard_rank=r, shard_count=S)
+        ix.loadCoarseQuantizer(Cq)
+        ix.loadProductQuantizer(P)
+        ix.setW(w)
+        lists, codes = ix.indexVectors(None, X, return_codes=True)  # every shard is offered every vector, keeps its lists
+        h = (C.c_ubyte * _capi.COMM_HANDLE_BYTES)()
+        check(lib.mmidx_comm_create(ix._h, r, S, S, 512, 16, h))
+        idx.append(ix)
+        handles.append(bytes(h))
+    for ix in idx:
+        check(lib.mmidx_comm_attach(ix._h, C.c_char_p(b"".join(handles))))
+    off, cc, ii = synth.csr_from_assignments(lists, codes, nlist)
+    oi, od, oc = O.ivfpq_search(Cq, P, off, cc, ii, Q, k, w)
+    sl = (nq + S - 1) // S
+    out = [None] * S
+    err = [None] * S
+
+    def rank_thread(r):
+        try:
+            for step in range(5):  # window parity, epochs, graph capture on the third step
+                ids = np.full((sl, k), -7, dtype=np.int32)
+                dd = np.zeros((sl, k))
+                cn = np.zeros(sl, dtype=np.int32)
+                fq, nr = C.c_int64(), C.c_int64()
+                check(lib.mmidx_search_multi(idx[r]._h, nq, C.c_void_p(Q.ctypes.data), k, C.c_void_p(ids.ctypes.data),
+                                             C.c_void_p(dd.ctypes.data), C.c_void_p(cn.ctypes.data), C.byref(fq), C.byref(nr)))
+                out[r] = (fq.value, nr.value, ids, dd, cn)
+        except Exception as e:  # noqa: BLE001
+            err[r] = repr(e)
+
+    ts = [threading.Thread(target=rank_thread, args=(r,)) for r in range(S)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert err == [None] * S, err
+    covered = 0
+    for r in range(S):
+        fq, nr, ids, dd, cn = out[r]
+        assert (ids[:nr] == oi[fq:fq + nr]).all() and (dd[:nr] == od[fq:fq + nr]).all() and (cn[:nr] == oc[fq:fq + nr]).all(), r
+        covered += nr
+    assert covered == nq
+    for ix in idx:
+        check(lib.mmidx_comm_destroy(ix._h))
+        ix.close()
