@@ -1041,6 +1041,12 @@ def run_gpu_cfg4(args, ctx, M, synth, wl):
     scan_ms = head["stage_ms_per_step"]["scan"]
     per_gpu_bytes = scan_bytes_total / world if world > 1 else scan_bytes_total
     achieved = per_gpu_bytes / (scan_ms * 1e-3) / 1e9
+    traffic4 = None  # DRAM bytes of one launch of the scan on ONE GPU holding the whole 10 M database (ncu, profiles/)
+    if world == 1 and N_DB == wl["N_DB"]:
+        try:
+            traffic4 = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic_cfg4.json")))["dram_bytes_per_step"]
+        except Exception:
+            traffic4 = None
     out = {
         "metric": "queries/sec", "value": head["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": 6, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
@@ -1051,7 +1057,7 @@ def run_gpu_cfg4(args, ctx, M, synth, wl):
         "step_ms_percentiles": head.get("step_ms_percentiles"),
         "stage_ms_per_step": head["stage_ms_per_step"],
         "roofline": {"bound": "hbm", "kernel": "k_ivfpq_scan_fast<2048,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic4, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": per_gpu_bytes, "kernel_ms_per_launch": scan_ms,
                      "note": "rank 0's launch; bytes = the job's probed-list bytes / shards (balanced map)"},
         "list_sharded": shd, "replicas": rep, "index_vectors_per_s": index_rate,
