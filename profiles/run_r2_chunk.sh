@@ -1,7 +1,7 @@
 #!/bin/bash
 # end-to-end (host buffers) step time of configs[2] against the chunk size of mmidx_search's copy/compute pipeline
 mkdir -p gpurun_out
-for ch in 2048 1024 1536 2560 3400 5000 2048; do
+for ch in ${CHUNKS:-2048 1024 1536 2560 3400 5000 2048}; do
   MMIDX_CHUNK=$ch timeout 600 python bench.py --steps 20 --warmup 6 --quick --no-cpu-baseline > gpurun_out/chunk_$ch.json 2> gpurun_out/chunk_$ch.err
   python - $ch <<'PY'
 import json, sys
