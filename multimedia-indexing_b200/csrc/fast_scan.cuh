@@ -818,16 +818,17 @@ __device__ __noinline__ void scan_list_rounds(TopK32<CAP32> &c32, const uint32_t
 }
 
 // grid (nsplit, nq).  CTA (s, q) handles owned probe slots s, s+nsplit, ... of query q in rank order.
-// Shared memory: TopK32 | t2 | lut[2] | qv.
-// Per probe: one independent descriptor load, wait for the TMA of the probe's T1 row -- it lands straight in the table
+// Shared memory: TopK32 | t2 | lut[2] | qv | mbarrier | the query's probe descriptors (when the host grants the room).
+// Per probe: one descriptor read, wait for the TMA of the probe's T1 row -- it lands straight in the table
 // buffer the previous probe is not using -- then the fp32 table lut = (T1[l] + T2) + s is built IN PLACE with 128-bit shared
 // accesses, ONE block barrier (which also settles the collector), the TMA of the next T1 row into the other buffer (its
 // last reader, the previous probe's sweep, ended at that barrier), then a barrier-free sweep over the list with the next
-// 128-bit code load in flight.  (No staging buffer: 33 KB per CTA at m = 8, 66 KB at m = 16 -- three CTAs per SM instead of two.)
+// 128-bit code load in flight.  (No staging buffer: 36 KB per CTA at m = 8, 69 KB at m = 16 -- three CTAs per SM instead of two;
+// the m = 16 instantiation is compiled for exactly those three, i.e. with 80 registers.)
 // LONG: some list is longer than FAST_SEG entries (the pseudo lists of a large flat PQ index: 10^5 entries).  Such lists are
 // swept in segments of FAST_SEG entries with a settle in between, so that the admission threshold is re-read while it
 // tightens and a collector overflow re-scans one segment, not the list (without this a 1 GiB flat scan ran at 25 % of the
-// HBM peak, with it at 41 % for one query and 63 % for eight: profiles/README.md).  IVF lists are short: the LONG = false
+// HBM peak, with it at 45 % for one query and 69 % for eight: profiles/README.md).  IVF lists are short: the LONG = false
 // instantiation is the kernel exactly as tuned for them.  (Also measured and rejected for the HBM-streaming regime: four
 // 128-bit loads in flight per thread at 3 CTAs/SM -- slower at every batch size.)
 constexpr int FAST_SEG = 8192;
